@@ -1,0 +1,1234 @@
+// api.cu -- the C ABI (include/ocffm.h) and the host-side schedule of the solver and evaluator.
+//
+// The schedule (which block, which half, W before H, CG stop test) is the reference's
+// (ffm.cpp:744-870); everything numeric runs in the kernels of rows.cu / dense.cu / eval.cu on
+// one CUDA stream.  There is no CPU code path for any of it: without a device, ocffm_create fails.
+//
+// Device layout (T = float or double, kp = padded k):
+//   W[f12] [D_f1 x kp], H[f12] [D_f2 x kp]              parameter blocks, replicated on every rank
+//   Pc [m x Kc], Qc [n x Kc], Kc = fu*fv*kp             cross-pair embeddings concatenated so that
+//                                                       pair p = a*fv + (b-fu) is columns [p*kp,(p+1)*kp)
+//   P[f12], Q[f12] [rows x kp]                          same-side embeddings (only with self_side)
+//   a [m], b [n], sa [m], sb [n]
+//   Omega twice: by user (CSR, U->Y) and by item (CSC, V->Y), each with its own y-tilde copy
+//   (ffm.cpp:393,400) and a work-item list (kernels.h OmegaView).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ocffm.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ocffm {
+
+thread_local uint64_t *g_launch_counter = nullptr;
+static thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time so that the library loads on hosts without NCCL and a single-GPU
+// context never touches it.
+// ---------------------------------------------------------------------------------------------
+struct Nccl {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+
+    static Nccl &get() {
+        static Nccl n;
+        if (!n.h) {
+            const char *names[] = {"libnccl.so.2", "libnccl.so"};
+            for (const char *nm : names) {
+                n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+                if (n.h) break;
+            }
+            if (!n.h) throw Error(OCFFM_E_COMM, std::string("cannot load libnccl: ") + dlerror());
+#define OC_SYM(field, name)                                                      \
+    n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.h, name));             \
+    if (!n.field) throw Error(OCFFM_E_COMM, std::string("missing NCCL symbol ") + name)
+            OC_SYM(GetUniqueId, "ncclGetUniqueId");
+            OC_SYM(CommInitRank, "ncclCommInitRank");
+            OC_SYM(CommDestroy, "ncclCommDestroy");
+            OC_SYM(AllReduce, "ncclAllReduce");
+            OC_SYM(Broadcast, "ncclBroadcast");
+            OC_SYM(GroupStart, "ncclGroupStart");
+            OC_SYM(GroupEnd, "ncclGroupEnd");
+            OC_SYM(GetErrorString, "ncclGetErrorString");
+#undef OC_SYM
+        }
+        return n;
+    }
+};
+
+#define OC_NCCL(expr)                                                                       \
+    do {                                                                                    \
+        ncclResult_t r__ = (expr);                                                          \
+        if (r__ != ncclSuccess)                                                             \
+            throw ::ocffm::Error(OCFFM_E_COMM, std::string(#expr) + ": " + ::ocffm::Nccl::get().GetErrorString(r__)); \
+    } while (0)
+
+template <typename T>
+ncclDataType_t nccl_type();
+template <>
+ncclDataType_t nccl_type<float>() { return ncclFloat; }
+template <>
+ncclDataType_t nccl_type<double>() { return ncclDouble; }
+
+struct Comm {
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    ~Comm() {
+        if (comm) Nccl::get().CommDestroy(comm);
+    }
+    bool active() const { return nranks > 1; }
+    template <typename T>
+    void allreduce(T *buf, size_t n, cudaStream_t s) {
+        if (!active() || !n) return;
+        OC_NCCL(Nccl::get().AllReduce(buf, buf, n, nccl_type<T>(), ncclSum, comm, s));
+    }
+    // all-gather of row slices with unequal sizes: rank q owns rows [lo(q), lo(q+1)) of a
+    // [rows x ld] matrix and broadcasts them to everyone (one grouped launch)
+    template <typename T>
+    void allgather_rows(T *buf, uint64_t rows, size_t ld, cudaStream_t s) {
+        if (!active()) return;
+        Nccl &n = Nccl::get();
+        OC_NCCL(n.GroupStart());
+        for (int q = 0; q < nranks; ++q) {
+            const uint64_t lo = rows * q / nranks, hi = rows * (q + 1) / nranks;
+            if (hi > lo)
+                OC_NCCL(n.Broadcast(buf + lo * ld, buf + lo * ld, (hi - lo) * ld, nccl_type<T>(), q,
+                                    comm, s));
+        }
+        OC_NCCL(n.GroupEnd());
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+struct CtxBase {
+    virtual ~CtxBase() {}
+    virtual void comm_init(int nranks, int rank, const void *id) = 0;
+    virtual void set_field(int side, uint32_t field, uint64_t rows, uint64_t D, const uint64_t *rowptr,
+                           const uint32_t *idx, const double *val) = 0;
+    virtual void set_labels(uint64_t m, const uint64_t *rowptr, const uint32_t *idx,
+                            const uint64_t *cp, const uint32_t *ri, uint64_t n_ranked,
+                            const double *popular) = 0;
+    virtual void set_test_labels(uint64_t mt, const uint64_t *rowptr, const uint32_t *idx,
+                                 const uint64_t *nnx) = 0;
+    virtual void set_block(uint32_t f1, uint32_t f2, int which, const double *data, uint64_t rows) = 0;
+    virtual void get_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) = 0;
+    virtual void init_state() = 0;
+    virtual void solve_block(uint32_t f1, uint32_t f2) = 0;
+    virtual void one_epoch() = 0;
+    virtual void grad(uint32_t f1, uint32_t f2, int which, double *G, uint64_t rows) = 0;
+    virtual void hess_vec(uint32_t f1, uint32_t f2, int which, const double *V, double *Hv,
+                          uint64_t rows) = 0;
+    virtual void cg(uint32_t f1, uint32_t f2, int which, const double *G, double *S, uint64_t rows,
+                    int32_t *iters) = 0;
+    virtual void objective(double *value) = 0;
+    virtual void validate(double *prec, double *ndcg, double *ploss, uint32_t *topk) = 0;
+    virtual void get_vec(const char *name, double *out, uint64_t *count) = 0;
+    virtual void get_embed(uint32_t f1, uint32_t f2, int which, double *out, uint64_t rows) = 0;
+    virtual void get_csc(uint64_t *colptr, uint32_t *rowidx) = 0;
+    virtual void get_stats(ocffm_stats *out) = 0;
+    virtual void reset_stats() = 0;
+    virtual void synchronize() = 0;
+    virtual void *stream() = 0;
+};
+
+static uint32_t pad_k(uint32_t k) {
+    uint32_t kp = 4;
+    while (kp < k) kp <<= 1;
+    return kp;
+}
+
+template <typename T>
+struct Problem final : CtxBase {
+    ocffm_params prm;
+    uint32_t fu, fv, f, k, kp, Fx, Kc;
+    uint64_t m, n, mt = 0, n_ranked = 0;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    Comm comm;
+    uint32_t chunk = 64;
+    bool profile = false;
+
+    struct Field {
+        bool set = false;
+        uint64_t rows = 0, D = 0, nnz = 0;
+        DevBuf<uint32_t> rowptr, idx;
+        DevBuf<T> val, freq;
+        uint32_t row0 = 0, row1 = 0;
+        CsrView<T> view() const { return {rowptr.p, idx.p, val.p, row0, row1}; }
+        CsrView<T> view_all() const { return {rowptr.p, idx.p, val.p, 0, uint32_t(rows)}; }
+    };
+    struct Omega {
+        bool set = false;
+        uint64_t rows = 0, nnz = 0, nnz_local = 0;
+        uint32_t n_items = 0, row0 = 0, row1 = 0;
+        DevBuf<uint32_t> rowptr, idx, wi_row, wi_beg, wi_cnt;
+        DevBuf<T> yt;
+        std::vector<uint64_t> h_rowptr;   // kept for get_csc / stats
+        std::vector<uint32_t> h_idx;
+        OmegaView<T> view() const {
+            return {wi_row.p, wi_beg.p, wi_cnt.p, n_items, rowptr.p, idx.p, yt.p, row0, row1, nnz_local};
+        }
+    };
+    struct Block {
+        bool exists = false, side = false, has_w = false, has_h = false;
+        uint32_t f1 = 0, f2 = 0;
+        int pair = -1;
+        DevBuf<T> W, H, P, Q;
+    };
+
+    std::vector<Field> XU, XV, XT;
+    Omega YU, YV;
+    DevBuf<uint32_t> t_rowptr, t_idx, topk_ids, cold_ids;
+    DevBuf<uint8_t> t_cold;
+    std::vector<uint8_t> h_cold;
+    bool test_set = false;
+    uint32_t t_row0 = 0, t_row1 = 0;
+    DevBuf<T> popular;
+    std::vector<double> h_popular;
+    std::vector<Block> blocks;
+    DevBuf<T> Pc, Qc, a, b, sa, sb;
+    bool state_ready = false;
+
+    // scratch
+    DevBuf<T> G, S, R, V, VQ, Hv, Tm, XS, gap, ysum, GT, oQ, bQ, vecKc;
+    DevBuf<double> gram64, acc64;
+    SolveScalars *sc = nullptr;
+    double *h_scal = nullptr;  // pinned
+
+    // stats
+    uint64_t launches = 0, cg_iters = 0, nnz_trav = 0, algo_bytes = 0, hv_launches = 0,
+             hv_algo_bytes = 0;
+    double ms[6] = {0, 0, 0, 0, 0, 0}, hv_ms = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hv_events;
+    size_t hv_events_used = 0;
+
+    Problem(const ocffm_params &p, uint32_t fu_, uint32_t fv_, uint64_t m_, uint64_t n_)
+        : prm(p), fu(fu_), fv(fv_), f(fu_ + fv_), k(p.k), m(m_), n(n_) {
+        OC_REQUIRE(fu >= 1 && fv >= 1, "need at least one user field and one item field");
+        OC_REQUIRE(k >= 1 && k <= 128, "k must be in 1..128");
+        OC_REQUIRE(m < (1ull << 31) && n < (1ull << 31), "row counts must be below 2^31");
+        kp = pad_k(k);
+        Fx = fu * fv;
+        Kc = Fx * kp;
+        if (p.device >= 0) OC_CUDA(cudaSetDevice(p.device));
+        OC_CUDA(cudaGetDevice(&device));
+        OC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        OC_CUDA(cudaMalloc(&sc, sizeof(SolveScalars)));
+        OC_CUDA(cudaMallocHost(&h_scal, 64 * sizeof(double)));
+        XU.resize(fu);
+        XV.resize(fv);
+        XT.resize(fu);
+        blocks.resize(size_t(f) * (f + 1) / 2);
+        for (uint32_t f1 = 0; f1 < f; ++f1)
+            for (uint32_t f2 = f1; f2 < f; ++f2) {
+                Block &bk = blocks[bidx(f1, f2)];
+                bk.f1 = f1;
+                bk.f2 = f2;
+                bk.side = (f1 < fu && f2 < fu) || (f1 >= fu && f2 >= fu);
+                bk.exists = prm.self_side || !bk.side;   // ffm.cpp:502-503
+                if (!bk.side) bk.pair = int(f1 * fv + (f2 - fu));
+            }
+        if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
+        if (const char *e = getenv("OCFFM_PROFILE")) profile = atoi(e) != 0;
+        a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
+        a.zero(st); b.zero(st); sa.zero(st); sb.zero(st);
+        Pc.alloc(m * Kc); Qc.alloc(n * Kc);
+        const uint64_t mx = std::max(m, n);
+        Tm.alloc(mx * kp); XS.alloc(mx * kp); gap.alloc(mx); ysum.alloc(mx);
+        GT.alloc(size_t(Kc) * kp); oQ.alloc(kp); bQ.alloc(kp); vecKc.alloc(Kc);
+        gram64.alloc(size_t(Kc) * kp + 2 * kp);
+        acc64.alloc(64);
+        sync();
+    }
+    ~Problem() override {
+        cudaSetDevice(device);
+        for (auto &e : hv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        if (sc) cudaFree(sc);
+        if (h_scal) cudaFreeHost(h_scal);
+        if (st) cudaStreamDestroy(st);
+    }
+
+    // index_vec, ffm.cpp:53-55
+    size_t bidx(uint32_t f1, uint32_t f2) const { return f2 + size_t(f - 1) * f1 - size_t(f1) * (f1 - 1) / 2; }
+    void sync() { OC_CUDA(cudaStreamSynchronize(st)); }
+    void bind() {
+        OC_CUDA(cudaSetDevice(device));
+        g_launch_counter = &launches;
+    }
+    Field &field_of(uint32_t fg) { return fg < fu ? XU[fg] : XV[fg - fu]; }
+    uint64_t rows_of(uint32_t fg) const { return fg < fu ? m : n; }
+    Block &block(uint32_t f1, uint32_t f2) {
+        OC_REQUIRE(f1 <= f2 && f2 < f, "block indices must satisfy f1 <= f2 < f");
+        Block &bk = blocks[bidx(f1, f2)];
+        OC_REQUIRE(bk.exists, "block does not exist (same-side block under --ns)");
+        return bk;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void comm_init(int nranks, int rank, const void *id) override {
+        OC_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+        OC_REQUIRE(!YU.set, "ocffm_comm_init must precede ocffm_set_labels");
+        comm.nranks = nranks;
+        comm.rank = rank;
+        if (nranks > 1) {
+            ncclUniqueId uid;
+            memcpy(&uid, id, sizeof(uid));
+            OC_NCCL(Nccl::get().CommInitRank(&comm.comm, nranks, uid, rank));
+        }
+    }
+    uint32_t lo(uint64_t rows) const { return uint32_t(rows * comm.rank / comm.nranks); }
+    uint32_t hi(uint64_t rows) const { return uint32_t(rows * (comm.rank + 1) / comm.nranks); }
+
+    void set_field(int side, uint32_t field, uint64_t rows, uint64_t D, const uint64_t *rowptr,
+                   const uint32_t *idx, const double *val) override {
+        OC_REQUIRE(side >= 0 && side <= 2, "side must be OCFFM_SIDE_U/V/T");
+        std::vector<Field> &vec = side == OCFFM_SIDE_U ? XU : side == OCFFM_SIDE_V ? XV : XT;
+        OC_REQUIRE(field < vec.size(), "field out of range");
+        const uint64_t want = side == OCFFM_SIDE_U ? m : side == OCFFM_SIDE_V ? n : rows;
+        OC_REQUIRE(rows == want, "row count does not match the context");
+        OC_REQUIRE(rows < (1ull << 31) && D < (1ull << 31), "sizes must be below 2^31");
+        const uint64_t nnz = rowptr[rows];
+        OC_REQUIRE(nnz < (1ull << 32), "nnz must be below 2^32");
+        Field &F = vec[field];
+        F.rows = rows; F.D = D; F.nnz = nnz;
+        std::vector<uint32_t> rp(rows + 1);
+        for (uint64_t i = 0; i <= rows; ++i) rp[i] = uint32_t(rowptr[i]);
+        std::vector<T> v(nnz), fr(D, T(0));
+        for (uint64_t t = 0; t < nnz; ++t) {
+            OC_REQUIRE(idx[t] < D, "feature index >= D");
+            v[t] = T(val[t]);
+            fr[idx[t]] += T(1);   // freq, ffm.cpp:235-241
+        }
+        F.rowptr.upload(rp, st);
+        F.idx.upload(idx, nnz, st);
+        F.val.upload(v, st);
+        F.freq.upload(fr, st);
+        F.row0 = lo(rows);
+        F.row1 = hi(rows);
+        F.set = true;
+        sync();
+        if (side == OCFFM_SIDE_T) { mt = rows; t_row0 = lo(rows); t_row1 = hi(rows); }
+        state_ready = false;
+    }
+
+    void build_omega(Omega &Y, uint64_t rows, const uint64_t *rowptr, const uint32_t *idx) {
+        Y.rows = rows;
+        Y.nnz = rowptr[rows];
+        OC_REQUIRE(Y.nnz < (1ull << 31), "|Omega| must be below 2^31");
+        Y.h_rowptr.assign(rowptr, rowptr + rows + 1);
+        Y.h_idx.assign(idx, idx + Y.nnz);
+        std::vector<uint32_t> rp(rows + 1);
+        for (uint64_t i = 0; i <= rows; ++i) rp[i] = uint32_t(rowptr[i]);
+        Y.row0 = lo(rows);
+        Y.row1 = hi(rows);
+        Y.nnz_local = rowptr[Y.row1] - rowptr[Y.row0];
+        std::vector<uint32_t> wr, wb, wc;
+        wr.reserve(Y.row1 - Y.row0 + Y.nnz_local / chunk);
+        wb.reserve(wr.capacity());
+        wc.reserve(wr.capacity());
+        for (uint32_t i = Y.row0; i < Y.row1; ++i) {
+            const uint64_t b0 = rowptr[i], e0 = rowptr[i + 1];
+            if (b0 == e0) { wr.push_back(i); wb.push_back(uint32_t(b0)); wc.push_back(0x80000000u); continue; }
+            for (uint64_t t = b0; t < e0; t += chunk) {
+                wr.push_back(i);
+                wb.push_back(uint32_t(t));
+                wc.push_back(uint32_t(std::min<uint64_t>(chunk, e0 - t)) | (t == b0 ? 0x80000000u : 0u));
+            }
+        }
+        Y.n_items = uint32_t(wr.size());
+        Y.rowptr.upload(rp, st);
+        Y.idx.upload(idx, Y.nnz, st);
+        Y.wi_row.upload(wr, st);
+        Y.wi_beg.upload(wb, st);
+        Y.wi_cnt.upload(wc, st);
+        Y.yt.alloc(Y.nnz);
+        Y.yt.zero(st);
+        Y.set = true;
+        sync();
+    }
+
+    void set_labels(uint64_t m_, const uint64_t *rowptr, const uint32_t *idx, const uint64_t *cp,
+                    const uint32_t *ri, uint64_t n_ranked_, const double *pop) override {
+        OC_REQUIRE(m_ == m, "label row count does not match the context");
+        const uint64_t nnz = rowptr[m];
+        build_omega(YU, m, rowptr, idx);
+        // U->n and popular (ffm.cpp:97, 143, 172-176)
+        uint64_t un = 0;
+        for (uint64_t t = 0; t < nnz; ++t) un = std::max<uint64_t>(un, uint64_t(idx[t]) + 1);
+        n_ranked = n_ranked_ ? n_ranked_ : un;
+        OC_REQUIRE(n_ranked >= un, "n_ranked smaller than max label + 1");
+        h_popular.assign(n_ranked, 0.0);
+        if (pop) {
+            std::copy(pop, pop + n_ranked, h_popular.begin());
+        } else {
+            for (uint64_t t = 0; t < nnz; ++t) h_popular[idx[t]] += 1.0;
+            double tot = 0;
+            for (double v : h_popular) tot += v;
+            for (double &v : h_popular) v /= tot;
+        }
+        std::vector<T> pv(h_popular.begin(), h_popular.end());
+        popular.upload(pv, st);
+        // CSC by (item, user): transY (ffm.cpp:259-294); labels >= n are dropped there
+        std::vector<uint64_t> colptr;
+        std::vector<uint32_t> rowidx;
+        if (!cp || !ri) {
+            colptr.assign(n + 1, 0);
+            uint64_t kept = 0;
+            for (uint64_t t = 0; t < nnz; ++t)
+                if (idx[t] < n) { colptr[idx[t] + 1]++; kept++; }
+            for (uint64_t j = 0; j < n; ++j) colptr[j + 1] += colptr[j];
+            rowidx.resize(kept);
+            std::vector<uint64_t> cur(colptr.begin(), colptr.end() - 1);
+            for (uint64_t i = 0; i < m; ++i)
+                for (uint64_t t = rowptr[i]; t < rowptr[i + 1]; ++t)
+                    if (idx[t] < n) rowidx[cur[idx[t]]++] = uint32_t(i);
+            cp = colptr.data();
+            ri = rowidx.data();
+        }
+        OC_REQUIRE(cp[n] == nnz, "labels >= number of items are not supported (the reference leaves "
+                                 "its two copies of Y inconsistent, ffm.cpp:267-268)");
+        build_omega(YV, n, cp, ri);
+        state_ready = false;
+    }
+
+    void set_test_labels(uint64_t mt_, const uint64_t *rowptr, const uint32_t *idx,
+                         const uint64_t *nnx) override {
+        for (uint32_t fi = 0; fi < fu; ++fi)
+            OC_REQUIRE(XT[fi].set && XT[fi].rows == mt_, "set every OCFFM_SIDE_T field first");
+        mt = mt_;
+        const uint64_t nnz = rowptr[mt];
+        OC_REQUIRE(nnz < (1ull << 31), "too many test labels");
+        std::vector<uint32_t> rp(mt + 1);
+        for (uint64_t i = 0; i <= mt; ++i) rp[i] = uint32_t(rowptr[i]);
+        t_rowptr.upload(rp, st);
+        t_idx.upload(idx, nnz, st);
+        h_cold.assign(mt, 0);
+        if (nnx) {
+            for (uint64_t i = 0; i < mt; ++i) h_cold[i] = nnx[i] == 0;
+        } else {
+            std::vector<uint64_t> cnt(mt, 0);
+            std::vector<uint32_t> frp;
+            for (uint32_t fi = 0; fi < fu; ++fi) {
+                frp.resize(mt + 1);
+                XT[fi].rowptr.download(frp.data(), mt + 1, st);
+                sync();
+                for (uint64_t i = 0; i < mt; ++i) cnt[i] += frp[i + 1] - frp[i];
+            }
+            for (uint64_t i = 0; i < mt; ++i) h_cold[i] = cnt[i] == 0;
+        }
+        t_cold.upload(h_cold, st);
+        topk_ids.alloc(mt * 80);
+        cold_ids.alloc(80);
+        t_row0 = lo(mt);
+        t_row1 = hi(mt);
+        sync();
+        test_set = true;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    DevBuf<T> &block_mat(Block &bk, int which) { return which == 'W' ? bk.W : bk.H; }
+    uint64_t block_rows(const Block &bk, int which) {
+        return which == 'W' ? field_of(bk.f1).D : field_of(bk.f2).D;
+    }
+    void upload_padded(DevBuf<T> &dst, const double *src, uint64_t rows) {
+        std::vector<T> h(rows * kp, T(0));
+        for (uint64_t i = 0; i < rows; ++i)
+            for (uint32_t d = 0; d < k; ++d) h[i * kp + d] = T(src[i * k + d]);
+        dst.upload(h, st);
+        sync();
+    }
+    void download_unpadded(const T *src, uint64_t ld, double *dst, uint64_t rows) {
+        std::vector<T> h(rows * ld);
+        OC_CUDA(cudaMemcpyAsync(h.data(), src, rows * ld * sizeof(T), cudaMemcpyDeviceToHost, st));
+        sync();
+        for (uint64_t i = 0; i < rows; ++i)
+            for (uint32_t d = 0; d < k; ++d) dst[i * k + d] = double(h[i * ld + d]);
+    }
+    void set_block(uint32_t f1, uint32_t f2, int which, const double *data, uint64_t rows) override {
+        OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
+        Block &bk = block(f1, f2);
+        OC_REQUIRE(field_of(which == 'W' ? f1 : f2).set, "set the block's field before its parameters");
+        OC_REQUIRE(rows == block_rows(bk, which), "rows must equal Ds of the block's field");
+        upload_padded(block_mat(bk, which), data, rows);
+        (which == 'W' ? bk.has_w : bk.has_h) = true;
+        state_ready = false;
+    }
+    void get_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) override {
+        OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
+        Block &bk = block(f1, f2);
+        OC_REQUIRE(which == 'W' ? bk.has_w : bk.has_h, "block was never set");
+        OC_REQUIRE(rows == block_rows(bk, which), "rows must equal Ds of the block's field");
+        download_unpadded(block_mat(bk, which).p, kp, data, rows);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // cache_sasb, ffm.cpp:514-535: sa = Pc colsum(Qc), sb = Qc colsum(Pc)
+    void cache_sasb() {
+        double *cs = gram64.p;   // >= Kc doubles
+        OC_CUDA(cudaMemsetAsync(cs, 0, Kc * sizeof(double), st));
+        col_sums<T>(Qc.p, Kc, Kc, 0, uint32_t(n), cs, st);
+        convert_from_f64<T>(cs, vecKc.p, Kc, st);
+        matvec_rows<T>(Pc.p, Kc, Kc, uint32_t(m), vecKc.p, sa.p, st);
+        OC_CUDA(cudaMemsetAsync(cs, 0, Kc * sizeof(double), st));
+        col_sums<T>(Pc.p, Kc, Kc, 0, uint32_t(m), cs, st);
+        convert_from_f64<T>(cs, vecKc.p, Kc, st);
+        matvec_rows<T>(Qc.p, Kc, Kc, uint32_t(n), vecKc.p, sb.p, st);
+        algo_bytes += uint64_t(Fx) * (m + n) * k * sizeof(T) + (m + n) * sizeof(T);
+    }
+
+    void init_state() override {
+        OC_REQUIRE(YU.set && YV.set, "labels not set");
+        for (auto &F : XU) OC_REQUIRE(F.set, "a user field is missing");
+        for (auto &F : XV) OC_REQUIRE(F.set, "an item field is missing");
+        for (auto &bk : blocks)
+            if (bk.exists) OC_REQUIRE(bk.has_w && bk.has_h, "a parameter block was never set");
+        // init_pair, ffm.cpp:346-349
+        for (auto &bk : blocks) {
+            if (!bk.exists) continue;
+            Field &X1 = field_of(bk.f1), &X2 = field_of(bk.f2);
+            if (bk.side) {
+                bk.P.alloc(X1.rows * kp);
+                bk.Q.alloc(X2.rows * kp);
+                spmm_rows<T>(X1.view_all(), bk.W.p, bk.P.p, kp, kp, st);
+                spmm_rows<T>(X2.view_all(), bk.H.p, bk.Q.p, kp, kp, st);
+            } else {
+                spmm_rows<T>(X1.view_all(), bk.W.p, Pc.p + size_t(bk.pair) * kp, Kc, kp, st);
+                spmm_rows<T>(X2.view_all(), bk.H.p, Qc.p + size_t(bk.pair) * kp, Kc, kp, st);
+            }
+        }
+        cache_sasb();                       // ffm.cpp:508
+        a.zero(st);
+        b.zero(st);
+        if (prm.self_side) {                // calc_side, ffm.cpp:360-373
+            for (auto &bk : blocks) {
+                if (!bk.exists || !bk.side) continue;
+                if (bk.f1 < fu) rowwise_dot<T>(bk.P.p, bk.Q.p, uint32_t(m), kp, a.p, 1, st);
+                else rowwise_dot<T>(bk.P.p, bk.Q.p, uint32_t(n), kp, b.p, 1, st);
+            }
+        }
+        // init_y_tilde, ffm.cpp:388-403, both copies
+        ytilde_base<T>(YU.view(), a.p, b.p, st);
+        ytilde_base<T>(YV.view(), b.p, a.p, st);
+        for (uint32_t p = 0; p < Fx; ++p) {
+            sddmm_add<T>(YU.view(), Pc.p + size_t(p) * kp, Kc, Qc.p + size_t(p) * kp, Kc, kp, st);
+            sddmm_add<T>(YV.view(), Qc.p + size_t(p) * kp, Kc, Pc.p + size_t(p) * kp, Kc, kp, st);
+        }
+        sync();
+        state_ready = true;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // one half of a block solve (the reference's (f1, W1, Q1, P1) argument tuples)
+    struct Half {
+        Block *bk;
+        bool side, user;   // user: the rows being swept are users
+        Field *X;
+        Omega *Yown, *Yoth;
+        uint64_t m1, n1, D;
+        T *W1, *Q1, *P1;
+        uint32_t ldq, ldp;
+        T *a1, *b1, *sa1;
+        const T *freq;
+    };
+    Half half_of(uint32_t f1, uint32_t f2, int which) {
+        OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
+        OC_REQUIRE(state_ready, "call ocffm_init_state first");
+        Block &bk = block(f1, f2);
+        Half h;
+        h.bk = &bk;
+        h.side = bk.side;
+        const uint32_t fa = which == 'W' ? f1 : f2;
+        h.user = fa < fu;
+        h.X = &field_of(fa);
+        h.Yown = h.user ? &YU : &YV;
+        h.Yoth = h.user ? &YV : &YU;
+        h.m1 = h.user ? m : n;
+        h.n1 = h.user ? n : m;
+        h.D = h.X->D;
+        h.a1 = h.user ? a.p : b.p;
+        h.b1 = h.user ? b.p : a.p;
+        h.sa1 = h.user ? sa.p : sb.p;
+        h.freq = prm.freq ? h.X->freq.p : nullptr;
+        if (bk.side) {
+            h.W1 = which == 'W' ? bk.W.p : bk.H.p;
+            h.Q1 = which == 'W' ? bk.Q.p : bk.P.p;
+            h.P1 = which == 'W' ? bk.P.p : bk.Q.p;
+            h.ldq = h.ldp = kp;
+        } else {
+            T *pslice = Pc.p + size_t(bk.pair) * kp, *qslice = Qc.p + size_t(bk.pair) * kp;
+            h.W1 = which == 'W' ? bk.W.p : bk.H.p;
+            h.Q1 = which == 'W' ? qslice : pslice;
+            h.P1 = which == 'W' ? pslice : qslice;
+            h.ldq = h.ldp = Kc;
+        }
+        const uint64_t len = h.D * kp;
+        G.ensure(len); S.ensure(len); R.ensure(len); V.ensure(len); VQ.ensure(len); Hv.ensure(len);
+        return h;
+    }
+
+    static uint64_t gather_bytes(uint64_t full, uint64_t rows_gathered, uint64_t row_bytes) {
+        return full <= (64ull << 20) ? full : rows_gathered * row_bytes;   // SURVEY.md 8 gather rule
+    }
+
+    // Gram stack + oQ + bQ of the companion side for a cross half (ffm.cpp:658-670 without the
+    // T accumulation; rows [pair*kp, (pair+1)*kp) of GT are QTQ of ffm.cpp:770)
+    void prepare_cross(const Half &h) {
+        const T *Qs = h.user ? Qc.p : Pc.p;   // the other side's concatenated embeddings
+        gram64.zero(st);
+        double *out = gram64.p, *cs = gram64.p + size_t(Kc) * kp, *wsum = cs + kp;
+        const uint32_t r0 = uint32_t(h.n1 * comm.rank / comm.nranks),
+                       r1 = uint32_t(h.n1 * (comm.rank + 1) / comm.nranks);
+        gram_stack<T>(Qs, Kc, Kc, h.Q1, h.ldq, kp, r0, r1, h.b1, out, cs, wsum, 0, st);
+        comm.allreduce(gram64.p, gram64.n, st);
+        convert_from_f64<T>(out, GT.p, size_t(Kc) * kp, st);
+        convert_from_f64<T>(cs, oQ.p, kp, st);
+        convert_from_f64<T>(wsum, bQ.p, kp, st);
+        algo_bytes += h.n1 * k * sizeof(T) * (Fx + 1);
+    }
+    const T *qtq_of(const Half &h) const { return GT.p + size_t(h.bk->pair) * kp * kp; }
+
+    // scatter part of the gradient into G (zeroed here); lambda W is added by cg_init
+    void grad_scatter(const Half &h) {
+        const size_t s = sizeof(T);
+        OC_CUDA(cudaMemsetAsync(G.p, 0, h.D * kp * sizeof(T), st));
+        const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        if (h.side) {
+            OC_CUDA(cudaMemsetAsync(ysum.p, 0, h.m1 * sizeof(T), st));
+            ytilde_rowsum<T>(h.Yown->view(), ysum.p, kp, st);
+            OC_CUDA(cudaMemsetAsync(&sc->bsum, 0, sizeof(double), st));
+            reduce_sum<T>(h.b1, h.n1, 0, &sc->bsum, st);
+            side_rows<T>(0, h.Yown->view(), h.X->view(), h.Q1, h.a1, h.sa1, ysum.p, &sc->bsum, nullptr,
+                         T(prm.omega), T(prm.r), T(h.n1), G.p, kp, st);
+            algo_bytes += nnzY * s + h.m1 * (k + 3) * s + nnzX * (4 + s) + 2 * h.D * k * s;
+        } else {
+            prepare_cross(h);
+            const T *Ps = h.user ? Pc.p : Qc.p;
+            const uint32_t r0 = h.Yown->row0, r1 = h.Yown->row1;
+            rowgemm<T>(Ps + size_t(r0) * Kc, Kc, Kc, GT.p, Tm.p + size_t(r0) * kp, r1 - r0, kp, st);
+            grad_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, Tm.p, h.a1, oQ.p, bQ.p,
+                               T(prm.omega), T(prm.r), G.p, kp, st);
+            algo_bytes += (h.m1 + 1) * 8 + nnzY * (4 + s) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
+                          uint64_t(Fx) * h.m1 * k * s + h.m1 * s + nnzX * (4 + s) + 2 * h.D * k * s;
+        }
+        comm.allreduce(G.p, h.D * kp, st);
+        nnz_trav += nnzY + nnzX;
+    }
+
+    size_t hv_event_pair() {
+        if (hv_events_used == hv_events.size()) {
+            cudaEvent_t e0, e1;
+            OC_CUDA(cudaEventCreate(&e0));
+            OC_CUDA(cudaEventCreate(&e1));
+            hv_events.emplace_back(e0, e1);
+        }
+        return hv_events_used++;
+    }
+    void drain_hv_events() {
+        for (size_t i = 0; i < hv_events_used; ++i) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, hv_events[i].first, hv_events[i].second) == cudaSuccess) hv_ms += t;
+        }
+        hv_events_used = 0;
+    }
+
+    // Hv (without the regulariser) for the direction in V; VQ must hold V QTQ for cross halves
+    void hess_scatter(const Half &h) {
+        const size_t s = sizeof(T);
+        const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        if (h.side) {
+            side_rows<T>(1, h.Yown->view(), h.X->view(), h.Q1, nullptr, nullptr, nullptr, nullptr, V.p,
+                         T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, st);
+            algo_bytes += nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) + h.m1 * k * s +
+                          h.m1 * 4 + h.D * k * s;
+            nnz_trav += nnzX;
+        } else {
+            rowgemm<T>(V.p, kp, kp, qtq_of(h), VQ.p, h.D, kp, st);
+            size_t ev = 0;
+            if (profile) {
+                if (hv_events_used >= 4096) { sync(); drain_hv_events(); }
+                ev = hv_event_pair();
+                OC_CUDA(cudaEventRecord(hv_events[ev].first, st));
+            }
+            hess_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega), Hv.p,
+                               kp, st);
+            if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
+            const uint64_t bytes = (h.m1 + 1) * 8 + nnzX * (4 + s) +
+                                   gather_bytes(h.D * k * s, nnzX, k * s) + nnzY * 4 +
+                                   gather_bytes(h.n1 * k * s, nnzY, k * s) + h.D * k * s;
+            algo_bytes += bytes;
+            hv_algo_bytes += bytes;
+            hv_launches++;
+            nnz_trav += nnzY + nnzX;
+        }
+        comm.allreduce(Hv.p, h.D * kp, st);
+    }
+
+    double read_scalar(const double *dev) {
+        OC_CUDA(cudaMemcpyAsync(h_scal, dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+        sync();
+        return h_scal[0];
+    }
+
+    // cg, ffm.cpp:744-813.  G holds the gradient WITHOUT lambda W when add_reg is set (solver
+    // path, the regulariser is fused into cg_init), or the full gradient otherwise.
+    int run_cg(const Half &h, bool add_reg) {
+        const uint64_t len = h.D * kp;
+        OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
+        cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, st);
+        const double g2 = read_scalar(&sc->r2[0]);
+        double r2 = g2;
+        int it = 0;
+        const int max_cg = 20;
+        const double eps = 9e-2;
+        while (g2 * eps < r2 && it < max_cg) {
+            cg_dir<T>(V.p, R.p, Hv.p, len, it, sc, st);
+            hess_scatter(h);
+            cg_reg_dot<T>(Hv.p, V.p, h.freq, T(prm.lambda), h.D, kp, it, sc, st);
+            cg_step<T>(S.p, R.p, V.p, Hv.p, len, it, sc, st);
+            algo_bytes += 7 * h.D * k * sizeof(T);
+            r2 = read_scalar(&sc->r2[it + 1]);
+            ++it;
+        }
+        cg_iters += uint64_t(it);
+        return it;
+    }
+
+    // update_side / update_cross, ffm.cpp:405-465
+    void apply_update(const Half &h) {
+        const size_t s = sizeof(T);
+        const uint64_t len = h.D * kp, nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        axpy<T>(h.W1, S.p, T(1), len, st);
+        const T *q_side = h.side ? h.Q1 : nullptr;
+        if (!comm.active()) {
+            spmm_update<T>(h.X->view_all(), S.p, XS.p, h.P1, h.ldp, q_side, gap.p, h.a1, kp, st);
+        } else {
+            spmm_rows<T>(h.X->view(), S.p, XS.p, kp, kp, st);
+            comm.allgather_rows(XS.p, h.m1, kp, st);
+            // P1 += XS (and the side terms) on every rank's replica
+            CsrView<T> none{nullptr, nullptr, nullptr, 0, 0};
+            (void)none;
+            spmm_update_from_xs(h, q_side);
+        }
+        if (h.side) {
+            ytilde_add_gap<T>(h.Yown->view(), gap.p, 1, st);
+            ytilde_add_gap<T>(h.Yoth->view(), gap.p, 0, st);
+            algo_bytes += 3 * h.D * k * s + nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) +
+                          4 * h.m1 * k * s + 2 * (nnzY * (4 + 2 * s) + h.m1 * s);
+        } else {
+            sddmm_add<T>(h.Yown->view(), XS.p, kp, h.Q1, h.ldq, kp, st);
+            sddmm_add<T>(h.Yoth->view(), h.Q1, h.ldq, XS.p, kp, kp, st);
+            algo_bytes += 3 * h.D * k * s + nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) +
+                          4 * h.m1 * k * s +
+                          2 * (nnzY * (4 + 2 * s) + gather_bytes(h.m1 * k * s, nnzY, k * s) +
+                               gather_bytes(h.n1 * k * s, nnzY, k * s));
+        }
+        nnz_trav += 2 * nnzY + nnzX;
+    }
+    // multi-rank variant of the tail of spmm_update: XS is complete on every rank
+    void spmm_update_from_xs(const Half &h, const T *q_side) {
+        // P1[row, :] += XS[row, :] for all rows: expressed as spmm_update over an identity pattern
+        // would cost an index array; use axpy for contiguous side blocks and a strided add otherwise
+        if (h.ldp == kp) {
+            axpy<T>(h.P1, XS.p, T(1), h.m1 * kp, st);
+        } else {
+            strided_add(h.P1, h.ldp, XS.p, h.m1);
+        }
+        if (q_side) {
+            rowwise_dot<T>(XS.p, q_side, uint32_t(h.m1), kp, gap.p, 0, st);
+            axpy_scalar_vec(h.a1, gap.p, h.m1);
+        }
+    }
+    void strided_add(T *dst, uint32_t ld, const T *src, uint64_t rows);
+    void axpy_scalar_vec(T *y, const T *x, uint64_t n_);
+
+    void solve_half(uint32_t f1, uint32_t f2, int which) {
+        Half h = half_of(f1, f2, which);
+        grad_scatter(h);
+        run_cg(h, true);
+        apply_update(h);
+    }
+    void solve_block(uint32_t f1, uint32_t f2) override {
+        solve_half(f1, f2, 'W');   // W first, then H against the updated P1 (ffm.cpp:826-832, 843-849)
+        solve_half(f1, f2, 'H');
+    }
+    void one_epoch() override {
+        OC_REQUIRE(state_ready, "call ocffm_init_state first");
+        if (prm.self_side) {
+            for (uint32_t f1 = 0; f1 < fu; ++f1)
+                for (uint32_t f2 = f1; f2 < fu; ++f2) solve_block(f1, f2);
+            for (uint32_t f1 = fu; f1 < f; ++f1)
+                for (uint32_t f2 = f1; f2 < f; ++f2) solve_block(f1, f2);
+        }
+        for (uint32_t f1 = 0; f1 < fu; ++f1)
+            for (uint32_t f2 = fu; f2 < f; ++f2) solve_block(f1, f2);
+        if (prm.self_side) cache_sasb();
+        sync();
+        if (profile) drain_hv_events();
+    }
+
+    // ---- observation entry points (parity tests) -------------------------------------------------
+    void add_reg_into(T *dst, const T *src, const Half &h) {
+        // dst += lambda (freq) src, via cg_reg_dot's first half would also touch scalars; reuse cg_init
+        // on a scratch is overkill -> small dedicated path through axpy when no freq
+        if (!h.freq) {
+            axpy<T>(dst, src, T(prm.lambda), h.D * kp, st);
+        } else {
+            OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
+            cg_reg_dot<T>(dst, src, h.freq, T(prm.lambda), h.D, kp, 0, sc, st);
+        }
+    }
+    void grad(uint32_t f1, uint32_t f2, int which, double *Gout, uint64_t rows) override {
+        Half h = half_of(f1, f2, which);
+        OC_REQUIRE(rows == h.D, "rows must equal Ds of the updated field");
+        grad_scatter(h);
+        add_reg_into(G.p, h.W1, h);
+        download_unpadded(G.p, kp, Gout, h.D);
+    }
+    void hess_vec(uint32_t f1, uint32_t f2, int which, const double *Vin, double *Hout,
+                  uint64_t rows) override {
+        Half h = half_of(f1, f2, which);
+        OC_REQUIRE(rows == h.D, "rows must equal Ds of the updated field");
+        upload_padded(V, Vin, h.D);
+        if (!h.side) prepare_cross(h);
+        OC_CUDA(cudaMemsetAsync(Hv.p, 0, h.D * kp * sizeof(T), st));
+        hess_scatter(h);
+        add_reg_into(Hv.p, V.p, h);
+        download_unpadded(Hv.p, kp, Hout, h.D);
+    }
+    void cg(uint32_t f1, uint32_t f2, int which, const double *Gin, double *Sout, uint64_t rows,
+            int32_t *iters) override {
+        Half h = half_of(f1, f2, which);
+        OC_REQUIRE(rows == h.D, "rows must equal Ds of the updated field");
+        upload_padded(G, Gin, h.D);
+        if (!h.side) prepare_cross(h);
+        const uint64_t before = cg_iters;
+        const int it = run_cg(h, false);
+        cg_iters = before;
+        if (iters) *iters = it;
+        download_unpadded(S.p, kp, Sout, h.D);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // func(), ffm.cpp:1321-1351, through Gram identities (see DESIGN.md "objective")
+    void objective(double *value) override {
+        OC_REQUIRE(state_ready, "call ocffm_init_state first");
+        const size_t gsz = size_t(Kc) * kp;
+        std::vector<double> PtP(size_t(Kc) * Kc), QtQ(size_t(Kc) * Kc), sP(Kc), sQ(Kc), Pa(Kc), Qb(Kc);
+        std::vector<double> tmp(gsz + 2 * kp);
+        auto side_grams = [&](const T *M, uint64_t rows, const T *wv, std::vector<double> &MtM,
+                              std::vector<double> &sM, std::vector<double> &Mw) {
+            for (uint32_t p = 0; p < Fx; ++p) {
+                gram64.zero(st);
+                gram_stack<T>(M, Kc, Kc, M + size_t(p) * kp, Kc, kp, 0, uint32_t(rows), wv, gram64.p,
+                              gram64.p + gsz, gram64.p + gsz + kp, 1, st);
+                gram64.download(tmp.data(), gsz + 2 * kp, st);
+                sync();
+                for (uint32_t c = 0; c < Kc; ++c)
+                    for (uint32_t d = 0; d < kp; ++d) MtM[size_t(c) * Kc + p * kp + d] = tmp[size_t(c) * kp + d];
+                for (uint32_t d = 0; d < kp; ++d) {
+                    sM[p * kp + d] = tmp[gsz + d];
+                    Mw[p * kp + d] = tmp[gsz + kp + d];
+                }
+            }
+        };
+        side_grams(Pc.p, m, a.p, PtP, sP, Pa);
+        side_grams(Qc.p, n, b.p, QtQ, sQ, Qb);
+        acc64.zero(st);
+        reduce_sum<T>(a.p, m, 0, acc64.p + 0, st);
+        reduce_sum<T>(a.p, m, 1, acc64.p + 1, st);
+        reduce_sum<T>(b.p, n, 0, acc64.p + 2, st);
+        reduce_sum<T>(b.p, n, 1, acc64.p + 3, st);
+        // Omega part over the local rows of the user orientation
+        {
+            const uint64_t b0 = YU.h_rowptr[YU.row0], e0 = YU.h_rowptr[YU.row1];
+            omega_objective<T>(YU.yt.p + b0, e0 - b0, T(prm.omega), T(prm.r), acc64.p + 4, st);
+        }
+        comm.allreduce(acc64.p + 4, 1, st);
+        for (auto &bk : blocks) {
+            if (!bk.exists) continue;
+            reduce_sum<T>(bk.W.p, bk.W.n, 1, acc64.p + 5, st);
+            reduce_sum<T>(bk.H.p, bk.H.n, 1, acc64.p + 5, st);
+        }
+        double h[8];
+        acc64.download(h, 8, st);
+        sync();
+        const double r = prm.r, w = prm.omega;
+        const double sa_ = h[0], saa = h[1], sb_ = h[2], sbb = h[3];
+        const double sc_ = sa_ - double(m) * r, scc = saa - 2 * r * sa_ + double(m) * r * r;
+        double fro = 0, cPsQ = 0, bQsP = 0;
+        for (size_t i = 0; i < PtP.size(); ++i) fro += PtP[i] * QtQ[i];
+        for (uint32_t c = 0; c < Kc; ++c) {
+            cPsQ += (Pa[c] - r * sP[c]) * sQ[c];
+            bQsP += Qb[c] * sP[c];
+        }
+        const double all = double(n) * scc + double(m) * sbb + 2 * sc_ * sb_ + fro + 2 * cPsQ + 2 * bQsP;
+        *value = 0.5 * (h[4] + w * all + prm.lambda * h[5]);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // validate(), ffm.cpp:925-1016
+    void validate(double *prec, double *ndcg, double *ploss, uint32_t *topk) override {
+        OC_REQUIRE(test_set, "test labels not set");
+        for (auto &bk : blocks)
+            if (bk.exists) OC_REQUIRE(bk.has_w && bk.has_h, "a parameter block was never set");
+        DevBuf<T> Pva, Qva, at, bt, t1, t2;
+        Pva.alloc(mt * Kc);
+        Qva.alloc(n * Kc);
+        at.alloc(mt); bt.alloc(n);
+        at.zero(st); bt.zero(st);
+        t1.alloc(std::max(mt, n) * kp);
+        t2.alloc(std::max(mt, n) * kp);
+        for (auto &bk : blocks) {           // ffm.cpp:932-963
+            if (!bk.exists) continue;
+            if (!bk.side) {
+                spmm_rows<T>(XT[bk.f1].view_all(), bk.W.p, Pva.p + size_t(bk.pair) * kp, Kc, kp, st);
+                spmm_rows<T>(XV[bk.f2 - fu].view_all(), bk.H.p, Qva.p + size_t(bk.pair) * kp, Kc, kp, st);
+            } else if (bk.f1 < fu) {
+                spmm_rows<T>(XT[bk.f1].view_all(), bk.W.p, t1.p, kp, kp, st);
+                spmm_rows<T>(XT[bk.f2].view_all(), bk.H.p, t2.p, kp, kp, st);
+                rowwise_dot<T>(t1.p, t2.p, uint32_t(mt), kp, at.p, 1, st);
+            } else {
+                spmm_rows<T>(XV[bk.f1 - fu].view_all(), bk.W.p, t1.p, kp, kp, st);
+                spmm_rows<T>(XV[bk.f2 - fu].view_all(), bk.H.p, t2.p, kp, kp, st);
+                rowwise_dot<T>(t1.p, t2.p, uint32_t(n), kp, bt.p, 1, st);
+            }
+        }
+        vector_topk<T>(popular.p, uint32_t(n_ranked), cold_ids.p, st);
+        score_topk<T>(Pva.p, Qva.p, Kc, bt.p, t_row0, t_row1, uint32_t(n_ranked), t_cold.p, topk_ids.p, st);
+        acc64.zero(st);
+        eval_metrics<T>(topk_ids.p, cold_ids.p, t_cold.p, t_rowptr.p, t_idx.p, t_row0, t_row1, Pva.p,
+                        Qva.p, Kc, at.p, bt.p, popular.p, uint32_t(n), uint32_t(n_ranked), acc64.p, st);
+        comm.allreduce(acc64.p, 16, st);
+        double h[16];
+        acc64.download(h, 16, st);
+        sync();
+        const int cut[5] = {5, 10, 20, 40, 80};
+        for (int s = 0; s < 5; ++s) {
+            prec[s] = h[s] / (double(mt) * cut[s]);      // ffm.cpp:1013
+            ndcg[s] = h[5 + s] / double(mt);             // ffm.cpp:1014
+        }
+        *ploss = std::sqrt(h[10] / double(mt));          // ffm.cpp:1002
+        if (topk) {
+            OC_REQUIRE(!comm.active(), "top-k ids are only returned by single-rank contexts");
+            topk_ids.download(topk, mt * 80, st);
+            uint32_t cold80[80];
+            cold_ids.download(cold80, 80, st);
+            sync();
+            for (uint64_t i = 0; i < mt; ++i)
+                if (h_cold[i]) memcpy(topk + i * 80, cold80, sizeof(cold80));
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void get_vec(const char *name, double *out, uint64_t *count) override {
+        const std::string s(name);
+        const T *src = nullptr;
+        uint64_t cnt = 0;
+        if (s == "a") { src = a.p; cnt = m; }
+        else if (s == "b") { src = b.p; cnt = n; }
+        else if (s == "sa") { src = sa.p; cnt = m; }
+        else if (s == "sb") { src = sb.p; cnt = n; }
+        else if (s == "ytilde_csr") { src = YU.yt.p; cnt = YU.nnz; }
+        else if (s == "ytilde_csc") { src = YV.yt.p; cnt = YV.nnz; }
+        else if (s == "popular") { src = popular.p; cnt = n_ranked; }
+        else throw Error(OCFFM_E_INVALID, "unknown vector name " + s);
+        if (count) *count = cnt;
+        if (!out) return;
+        std::vector<T> h(cnt);
+        OC_CUDA(cudaMemcpyAsync(h.data(), src, cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+        sync();
+        for (uint64_t i = 0; i < cnt; ++i) out[i] = double(h[i]);
+    }
+    void get_embed(uint32_t f1, uint32_t f2, int which, double *out, uint64_t rows) override {
+        OC_REQUIRE(which == 'P' || which == 'Q', "which must be 'P' or 'Q'");
+        OC_REQUIRE(state_ready, "call ocffm_init_state first");
+        Block &bk = block(f1, f2);
+        const uint64_t want = which == 'P' ? rows_of(f1) : rows_of(f2);
+        OC_REQUIRE(rows == want, "rows must equal the row count of the embedding's side");
+        if (bk.side) download_unpadded(which == 'P' ? bk.P.p : bk.Q.p, kp, out, rows);
+        else {
+            // strided slice: copy the whole concatenated matrix rows then pick the columns
+            const T *base = (which == 'P' ? Pc.p : Qc.p);
+            std::vector<T> h(rows * Kc);
+            OC_CUDA(cudaMemcpyAsync(h.data(), base, rows * Kc * sizeof(T), cudaMemcpyDeviceToHost, st));
+            sync();
+            for (uint64_t i = 0; i < rows; ++i)
+                for (uint32_t d = 0; d < k; ++d) out[i * k + d] = double(h[i * Kc + size_t(bk.pair) * kp + d]);
+        }
+    }
+    void get_csc(uint64_t *colptr, uint32_t *rowidx) override {
+        OC_REQUIRE(YV.set, "labels not set");
+        std::vector<uint32_t> rp(n + 1), ix(YV.nnz);
+        YV.rowptr.download(rp.data(), n + 1, st);
+        YV.idx.download(ix.data(), YV.nnz, st);
+        sync();
+        for (uint64_t j = 0; j <= n; ++j) colptr[j] = rp[j];
+        std::copy(ix.begin(), ix.end(), rowidx);
+    }
+    void get_stats(ocffm_stats *out) override {
+        drain_hv_events();
+        memset(out, 0, sizeof(*out));
+        out->kernel_launches = launches;
+        out->cg_iters = cg_iters;
+        out->nnz_traversed = nnz_trav;
+        out->algo_bytes = algo_bytes;
+        out->hv_launches = hv_launches;
+        out->hv_algo_bytes = hv_algo_bytes;
+        out->hv_ms = hv_ms;
+    }
+    void reset_stats() override {
+        sync();
+        drain_hv_events();
+        launches = cg_iters = nnz_trav = algo_bytes = hv_launches = hv_algo_bytes = 0;
+        hv_ms = 0;
+    }
+    void synchronize() override { sync(); }
+    void *stream() override { return st; }
+};
+
+// small element-wise helpers used only by the multi-rank update path
+template <typename T>
+__global__ void k_strided_add(T *dst, uint32_t ld, const T *src, uint64_t rows, uint32_t kp) {
+    const uint64_t nvec = rows * (kp / 4);
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / (kp / 4), c = (i % (kp / 4)) * 4;
+        V4<T> d = ld4(dst + row * ld + c);
+        const V4<T> s = ld4(src + row * kp + c);
+        d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+        st4(dst + row * ld + c, d);
+    }
+}
+template <typename T>
+__global__ void k_vec_add(T *y, const T *x, uint64_t n) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x)
+        y[i] += x[i];
+}
+template <typename T>
+void Problem<T>::strided_add(T *dst, uint32_t ld, const T *src, uint64_t rows) {
+    if (!rows) return;
+    const uint64_t nvec = rows * (kp / 4);
+    OC_LAUNCH((k_strided_add<T>), unsigned(std::min<uint64_t>((nvec + 255) / 256, kSMs * 8)), 256, 0, st,
+              dst, ld, src, rows, kp);
+}
+template <typename T>
+void Problem<T>::axpy_scalar_vec(T *y, const T *x, uint64_t n_) {
+    if (!n_) return;
+    OC_LAUNCH((k_vec_add<T>), unsigned(std::min<uint64_t>((n_ + 255) / 256, kSMs * 8)), 256, 0, st, y, x, n_);
+}
+
+}  // namespace ocffm
+
+// ===============================================================================================
+// C ABI
+// ===============================================================================================
+struct ocffm_ctx {
+    std::unique_ptr<ocffm::CtxBase> impl;
+};
+
+namespace {
+template <typename F>
+int guarded(F &&fn) {
+    try {
+        fn();
+        return OCFFM_OK;
+    } catch (const ocffm::Error &e) {
+        ocffm::g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        ocffm::g_last_error = "host allocation failed";
+        return OCFFM_E_NOMEM;
+    } catch (const std::exception &e) {
+        ocffm::g_last_error = e.what();
+        return OCFFM_E_INVALID;
+    } catch (...) {
+        ocffm::g_last_error = "unknown error";
+        return OCFFM_E_INVALID;
+    }
+}
+template <typename T>
+ocffm::Problem<T> *as(ocffm_ctx *c) { return static_cast<ocffm::Problem<T> *>(c->impl.get()); }
+}  // namespace
+
+#define OC_CTX(ctx)                                                                    \
+    if (!(ctx) || !(ctx)->impl) {                                                      \
+        ocffm::g_last_error = "null context";                                          \
+        return OCFFM_E_INVALID;                                                        \
+    }
+
+template <typename F>
+static int with_ctx(ocffm_ctx *ctx, F &&fn) {
+    OC_CTX(ctx);
+    return guarded([&] {
+        // bind the device and the launch counter for this thread
+        if (auto *p = dynamic_cast<ocffm::Problem<float> *>(ctx->impl.get())) p->bind();
+        else if (auto *q = dynamic_cast<ocffm::Problem<double> *>(ctx->impl.get())) q->bind();
+        fn(*ctx->impl);
+    });
+}
+
+extern "C" {
+
+int ocffm_abi_version(void) { return OCFFM_ABI_VERSION; }
+const char *ocffm_last_error(void) { return ocffm::g_last_error.c_str(); }
+
+int ocffm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ocffm_create(ocffm_ctx **out, const ocffm_params *prm, uint32_t fu, uint32_t fv, uint64_t m,
+                 uint64_t n) {
+    if (!out || !prm) {
+        ocffm::g_last_error = "null argument";
+        return OCFFM_E_INVALID;
+    }
+    *out = nullptr;
+    return guarded([&] {
+        if (ocffm_device_count() <= 0)
+            throw ocffm::Error(OCFFM_E_NODEVICE,
+                               "no CUDA device: libocffm_cuda has no CPU fallback (sm_100a only)");
+        auto ctx = std::make_unique<ocffm_ctx>();
+        if (prm->dtype == OCFFM_F32) ctx->impl.reset(new ocffm::Problem<float>(*prm, fu, fv, m, n));
+        else if (prm->dtype == OCFFM_F64) ctx->impl.reset(new ocffm::Problem<double>(*prm, fu, fv, m, n));
+        else throw ocffm::Error(OCFFM_E_INVALID, "dtype must be OCFFM_F32 or OCFFM_F64");
+        *out = ctx.release();
+    });
+}
+
+int ocffm_destroy(ocffm_ctx *ctx) {
+    if (!ctx) return OCFFM_OK;
+    return guarded([&] { delete ctx; });
+}
+
+int ocffm_comm_unique_id(void *id128) {
+    return guarded([&] {
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        ncclUniqueId uid;
+        OC_NCCL(ocffm::Nccl::get().GetUniqueId(&uid));
+        memcpy(id128, &uid, sizeof(uid));
+    });
+}
+int ocffm_comm_init(ocffm_ctx *ctx, int nranks, int rank, const void *id128) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.comm_init(nranks, rank, id128); });
+}
+int ocffm_set_field(ocffm_ctx *ctx, int side, uint32_t field, uint64_t rows, uint64_t D,
+                    const uint64_t *rowptr, const uint32_t *idx, const double *val) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(rowptr && (idx || rowptr[rows] == 0) && (val || rowptr[rows] == 0), "null array");
+        c.set_field(side, field, rows, D, rowptr, idx, val);
+    });
+}
+int ocffm_set_labels(ocffm_ctx *ctx, uint64_t m, const uint64_t *rowptr, const uint32_t *idx,
+                     const uint64_t *csc_colptr, const uint32_t *csc_rowidx, uint64_t n_ranked,
+                     const double *popular) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(rowptr, "null array");
+        c.set_labels(m, rowptr, idx, csc_colptr, csc_rowidx, n_ranked, popular);
+    });
+}
+int ocffm_set_test_labels(ocffm_ctx *ctx, uint64_t m_t, const uint64_t *rowptr, const uint32_t *idx,
+                          const uint64_t *nnx) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(rowptr, "null array");
+        c.set_test_labels(m_t, rowptr, idx, nnx);
+    });
+}
+int ocffm_set_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, const double *data,
+                    uint64_t rows) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(data, "null array");
+        c.set_block(f1, f2, which, data, rows);
+    });
+}
+int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(data, "null array");
+        c.get_block(f1, f2, which, data, rows);
+    });
+}
+int ocffm_init_state(ocffm_ctx *ctx) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.init_state(); });
+}
+int ocffm_solve_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        c.solve_block(f1, f2);
+        c.synchronize();
+    });
+}
+int ocffm_one_epoch(ocffm_ctx *ctx) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.one_epoch(); });
+}
+int ocffm_grad(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double *G, uint64_t rows) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.grad(f1, f2, which, G, rows); });
+}
+int ocffm_hess_vec(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, const double *V, double *Hv,
+                   uint64_t rows) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.hess_vec(f1, f2, which, V, Hv, rows); });
+}
+int ocffm_cg(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, const double *G, double *S,
+             uint64_t rows, int32_t *iters) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.cg(f1, f2, which, G, S, rows, iters); });
+}
+int ocffm_objective(ocffm_ctx *ctx, double *value) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.objective(value); });
+}
+int ocffm_validate(ocffm_ctx *ctx, double *prec, double *ndcg, double *ploss, uint32_t *topk) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(prec && ndcg && ploss, "null output");
+        c.validate(prec, ndcg, ploss, topk);
+    });
+}
+int ocffm_get_vec(ocffm_ctx *ctx, const char *name, double *out, uint64_t *count) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        OC_REQUIRE(name, "null name");
+        c.get_vec(name, out, count);
+    });
+}
+int ocffm_get_embed(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double *out, uint64_t rows) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.get_embed(f1, f2, which, out, rows); });
+}
+int ocffm_get_csc(ocffm_ctx *ctx, uint64_t *colptr, uint32_t *rowidx) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.get_csc(colptr, rowidx); });
+}
+int ocffm_get_stats(ocffm_ctx *ctx, ocffm_stats *out) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) {
+        c.synchronize();
+        c.get_stats(out);
+    });
+}
+int ocffm_reset_stats(ocffm_ctx *ctx) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.reset_stats(); });
+}
+int ocffm_synchronize(ocffm_ctx *ctx) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.synchronize(); });
+}
+int ocffm_stream(ocffm_ctx *ctx, void **stream) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { *stream = c.stream(); });
+}
+
+}  // extern "C"

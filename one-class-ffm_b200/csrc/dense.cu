@@ -1,0 +1,505 @@
+// dense.cu -- the dense pieces of the solver (north_star subsystem 2 and the CG vector algebra):
+// stacked Gram contractions A^T B for all cross pairs at once, the tall-skinny row GEMMs
+// (T = P~ Gstack, VQTQ = V QTQ), the fused CG vector updates with device-resident fp64 scalars,
+// and small reductions.  SIMT FP32/FP64 with register micro-tiles staged through shared memory;
+// every global scalar is accumulated in fp64 ("Precision vs the 1e-4 tolerance").
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ocffm {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// Gram: Out64[kc, c] += sum_rows A[row, kc] * B[row, c]      (k x k per pair, stacked over pairs)
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename ACC, int KP, int TA, int TB>
+__global__ void __launch_bounds__(kThreads)
+k_gram(const T *__restrict__ A, uint32_t lda, uint32_t Kc, const T *__restrict__ B, uint32_t ldb,
+       uint32_t row0, uint32_t row1, const T *__restrict__ wvec, double *__restrict__ Out64,
+       double *__restrict__ colsum64, double *__restrict__ wsum64, uint32_t rows_per_cta) {
+    constexpr int NB = KP / TB;          // threads along the B columns
+    constexpr int NA = kThreads / NB;    // threads along the A columns
+    constexpr int KCH = NA * TA;         // A columns handled by one CTA (blockIdx.y picks the chunk)
+    // rows per shared-memory tile (static shared memory must stay under 48 KB)
+    constexpr int BR = (sizeof(T) * (KCH + 4 + KP) * 32 > 40000) ? 16 : 32;
+    __shared__ __align__(16) T As[BR][KCH + 4];
+    __shared__ __align__(16) T Bs[BR][KP];
+    __shared__ T ws[BR];
+    const int tid = threadIdx.x, tb = tid % NB, ta = tid / NB;
+    const uint32_t kc0 = blockIdx.y * KCH;
+    ACC acc[TA][TB];
+#pragma unroll
+    for (int i = 0; i < TA; ++i)
+#pragma unroll
+        for (int j = 0; j < TB; ++j) acc[i][j] = ACC(0);
+    ACC cs = ACC(0), wsa = ACC(0);
+    const uint64_t rbeg = uint64_t(row0) + uint64_t(blockIdx.x) * rows_per_cta;
+    const uint64_t rend = min(uint64_t(row1), rbeg + rows_per_cta);
+    for (uint64_t r0 = rbeg; r0 < rend; r0 += BR) {
+        for (int e = tid; e < BR * (KCH / 4); e += kThreads) {
+            const int r = e / (KCH / 4), c = (e % (KCH / 4)) * 4;
+            V4<T> v = zero4<T>();
+            if (r0 + r < rend && kc0 + c < Kc) v = ldg4(A + (r0 + r) * lda + kc0 + c);
+            st4(&As[r][c], v);
+        }
+        for (int e = tid; e < BR * (KP / 4); e += kThreads) {
+            const int r = e / (KP / 4), c = (e % (KP / 4)) * 4;
+            V4<T> v = zero4<T>();
+            if (r0 + r < rend) v = ldg4(B + (r0 + r) * ldb + c);
+            st4(&Bs[r][c], v);
+        }
+        if (tid < BR) ws[tid] = (wvec && r0 + tid < rend) ? wvec[r0 + tid] : T(0);
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < BR; ++r) {
+            T a[TA], b[TB];
+#pragma unroll
+            for (int i = 0; i < TA; ++i) a[i] = As[r][ta * TA + i];
+#pragma unroll
+            for (int j = 0; j < TB; ++j) b[j] = Bs[r][tb * TB + j];
+#pragma unroll
+            for (int i = 0; i < TA; ++i)
+#pragma unroll
+                for (int j = 0; j < TB; ++j) acc[i][j] += ACC(a[i]) * ACC(b[j]);
+        }
+        if (blockIdx.y == 0 && tid < KP && colsum64) {
+            for (int r = 0; r < BR; ++r) {
+                const ACC bv = ACC(Bs[r][tid]);
+                cs += bv;
+                wsa += ACC(ws[r]) * bv;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TA; ++i) {
+        const uint32_t kc = kc0 + ta * TA + i;
+        if (kc < Kc) {
+#pragma unroll
+            for (int j = 0; j < TB; ++j)
+                atomicAdd(Out64 + size_t(kc) * KP + tb * TB + j, double(acc[i][j]));
+        }
+    }
+    if (blockIdx.y == 0 && tid < KP && colsum64) {
+        atomicAdd(colsum64 + tid, double(cs));
+        if (wsum64) atomicAdd(wsum64 + tid, double(wsa));
+    }
+}
+
+template <typename T, typename ACC, int KP, int TA, int TB>
+void launch_gram(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, uint32_t row0,
+                 uint32_t row1, const T *wvec, double *Out64, double *colsum64, double *wsum64,
+                 cudaStream_t s) {
+    constexpr int NB = KP / TB, NA = kThreads / NB, KCH = NA * TA;
+    const uint32_t ny = (Kc + KCH - 1) / KCH;
+    const uint64_t rows = row1 - row0;
+    uint64_t slabs = std::min<uint64_t>((rows + 31) / 32, std::max<uint64_t>(1, (4 * kSMs) / ny));
+    uint32_t per = uint32_t((rows + slabs - 1) / slabs);
+    per = (per + 31) / 32 * 32;
+    slabs = (rows + per - 1) / per;
+    OC_LAUNCH((k_gram<T, ACC, KP, TA, TB>), dim3(unsigned(slabs), ny), kThreads, 0, s, A, lda, Kc, B,
+              ldb, row0, row1, wvec, Out64, colsum64, wsum64, per);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row GEMM: C[M x KP] = A[M x Ka] * B[Ka x KP], B tiny (Ka <= a few hundred), A streamed once.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KP, int TM, int TN>
+__global__ void __launch_bounds__(kThreads)
+k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restrict__ B,
+          T *__restrict__ C, uint64_t M) {
+    constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
+    constexpr int BK = sizeof(T) == 8 ? 16 : 32;   // keeps static shared memory under 48 KB
+    __shared__ __align__(16) T As[BK][BM + 4];
+    __shared__ __align__(16) T Bs[BK][KP];
+    const int tid = threadIdx.x, tn = tid % NN, tm = tid / NN;
+    const uint64_t m0 = uint64_t(blockIdx.x) * BM;
+    T acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+    for (uint32_t k0 = 0; k0 < Ka; k0 += BK) {
+        for (int e = tid; e < BM * (BK / 4); e += kThreads) {
+            const int r = e / (BK / 4), c = (e % (BK / 4)) * 4;
+            V4<T> v = zero4<T>();
+            if (m0 + r < M && k0 + c < Ka) v = ldg4(A + (m0 + r) * lda + k0 + c);
+            As[c + 0][r] = v.x;
+            As[c + 1][r] = v.y;
+            As[c + 2][r] = v.z;
+            As[c + 3][r] = v.w;
+        }
+        for (int e = tid; e < BK * (KP / 4); e += kThreads) {
+            const int kk = e / (KP / 4), c = (e % (KP / 4)) * 4;
+            V4<T> v = zero4<T>();
+            if (k0 + kk < Ka) v = ldg4(B + size_t(k0 + kk) * KP + c);
+            st4(&Bs[kk][c], v);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][tm * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tn * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const uint64_t row = m0 + tm * TM + i;
+        if (row < M) {
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                V4<T> v = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
+                st4(C + row * KP + tn * TN + j, v);
+            }
+        }
+    }
+}
+
+template <typename T, int KP, int TM, int TN>
+void launch_rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M,
+                    cudaStream_t s) {
+    constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
+    OC_LAUNCH((k_rowgemm<T, KP, TM, TN>), unsigned((M + BM - 1) / BM), kThreads, 0, s, A, lda, Ka, B,
+              C, M);
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise + reductions
+// ---------------------------------------------------------------------------------------------
+inline unsigned ew_blocks(uint64_t n_vec) {
+    return unsigned(std::max<uint64_t>(1, std::min<uint64_t>((n_vec + kThreads - 1) / kThreads,
+                                                             uint64_t(kSMs) * 8)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_convert(const double *__restrict__ src, T *__restrict__ dst, uint64_t n) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x)
+        dst[i] = T(src[i]);
+}
+
+
+// Deterministic grid-wide fp64 sum: block partials are combined by the last block to finish in
+// a fixed order, so CG scalars (and therefore the stop test ffm.cpp:780) are bit-identical on
+// every rank that holds the same replicated vectors.
+__device__ __forceinline__ void finish_sum(double local, SolveScalars *sc, double *out) {
+    __shared__ bool is_last;
+    local = block_sum(local);
+    if (threadIdx.x == 0) {
+        sc->partials[blockIdx.x] = local;
+        __threadfence();
+        const unsigned t = atomicInc(&sc->counter[0], gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double sum = 0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+            sum += reinterpret_cast<volatile double *>(sc->partials)[i];
+        sum = block_sum(sum);
+        if (threadIdx.x == 0) *out = sum;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_cg_init(T *__restrict__ G, const T *__restrict__ W, const T *__restrict__ freq, T lambda,
+          T *__restrict__ R, T *__restrict__ V, T *__restrict__ S, uint64_t nvec, int kp4,
+          SolveScalars *sc) {
+    double local = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const T c = freq ? lambda * freq[i / kp4] : lambda;
+        V4<T> g = ld4(G + i * 4);
+        const V4<T> w = ld4(W + i * 4);
+        g.x += c * w.x; g.y += c * w.y; g.z += c * w.z; g.w += c * w.w;
+        st4(G + i * 4, g);
+        const V4<T> r = {-g.x, -g.y, -g.z, -g.w};
+        st4(R + i * 4, r);
+        st4(V + i * 4, r);
+        st4(S + i * 4, zero4<T>());
+        local += double(g.x) * g.x + double(g.y) * g.y + double(g.z) * g.z + double(g.w) * g.w;
+    }
+    finish_sum(local, sc, &sc->r2[0]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_cg_dir(T *__restrict__ V, const T *__restrict__ R, T *__restrict__ Hv, uint64_t nvec, int it,
+         const SolveScalars *sc) {
+    const T beta = it > 0 ? T(sc->r2[it] / sc->r2[it - 1]) : T(0);
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        if (it > 0) {
+            const V4<T> r = ld4(R + i * 4);
+            V4<T> v = ld4(V + i * 4);
+            v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
+            st4(V + i * 4, v);
+        }
+        st4(Hv + i * 4, zero4<T>());
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_cg_reg_dot(T *__restrict__ Hv, const T *__restrict__ V, const T *__restrict__ freq, T lambda,
+             uint64_t nvec, int kp4, int it, SolveScalars *sc) {
+    double local = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const T c = freq ? lambda * freq[i / kp4] : lambda;
+        V4<T> h = ld4(Hv + i * 4);
+        const V4<T> v = ld4(V + i * 4);
+        h.x += c * v.x; h.y += c * v.y; h.z += c * v.z; h.w += c * v.w;
+        st4(Hv + i * 4, h);
+        local += double(v.x) * h.x + double(v.y) * h.y + double(v.z) * h.z + double(v.w) * h.w;
+    }
+    finish_sum(local, sc, &sc->vHv[it]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T *__restrict__ Hv,
+          uint64_t nvec, int it, SolveScalars *sc) {
+    const T alpha = T(sc->r2[it] / sc->vHv[it]);
+    double local = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const V4<T> v = ld4(V + i * 4), h = ld4(Hv + i * 4);
+        V4<T> sv = ld4(S + i * 4), r = ld4(R + i * 4);
+        sv.x += alpha * v.x; sv.y += alpha * v.y; sv.z += alpha * v.z; sv.w += alpha * v.w;
+        r.x -= alpha * h.x; r.y -= alpha * h.y; r.z -= alpha * h.z; r.w -= alpha * h.w;
+        st4(S + i * 4, sv);
+        st4(R + i * 4, r);
+        local += double(r.x) * r.x + double(r.y) * r.y + double(r.z) * r.z + double(r.w) * r.w;
+    }
+    finish_sum(local, sc, &sc->r2[it + 1]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_axpy(T *__restrict__ y, const T *__restrict__ x, T alpha, uint64_t nvec) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        V4<T> a = ld4(y + i * 4);
+        const V4<T> b = ld4(x + i * 4);
+        a.x += alpha * b.x; a.y += alpha * b.y; a.z += alpha * b.z; a.w += alpha * b.w;
+        st4(y + i * 4, a);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_reduce_sum(const T *__restrict__ x, uint64_t n, int square, double *out64) {
+    double local = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const double v = double(x[i]);
+        local += square ? v * v : v;
+    }
+    local = block_sum(local);
+    if (threadIdx.x == 0) atomicAdd(out64, local);
+}
+
+// column sums of a [rows x cols] slice (lda leading dimension): thread c%cols owns a column phase
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_col_sums(const T *__restrict__ A, uint32_t lda, uint32_t cols, uint32_t row0, uint32_t row1,
+           double *out64, uint32_t rows_per_cta) {
+    const uint64_t rbeg = uint64_t(row0) + uint64_t(blockIdx.x) * rows_per_cta;
+    const uint64_t rend = min(uint64_t(row1), rbeg + rows_per_cta);
+    const uint32_t lanes_per_row = min(cols, uint32_t(kThreads));
+    const uint32_t rows_in_flight = kThreads / lanes_per_row;
+    const uint32_t c0 = threadIdx.x % lanes_per_row, rsub = threadIdx.x / lanes_per_row;
+    if (rsub >= rows_in_flight) return;
+    for (uint32_t c = c0; c < cols; c += lanes_per_row) {
+        double local = 0;
+        for (uint64_t r = rbeg + rsub; r < rend; r += rows_in_flight) local += double(A[r * lda + c]);
+        atomicAdd(out64 + c, local);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_matvec_rows(const T *__restrict__ A, uint32_t lda, uint32_t cols, uint32_t rows,
+              const T *__restrict__ v, T *__restrict__ out) {
+    const uint64_t row = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    T acc = T(0);
+    for (uint32_t c = lane * 4; c < cols; c += 128) acc += dot4(ldg4(A + row * lda + c), ldg4(v + c));
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_omega_objective(const T *__restrict__ yt, uint64_t nnz, T w, T r, double *out64) {
+    double local = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const double y = double(yt[i]);
+        const double e = y + 1.0 - double(r);
+        local += y * y - double(w) * e * e;
+    }
+    local = block_sum(local);
+    if (threadIdx.x == 0) atomicAdd(out64, local);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, int kp,
+                uint32_t row0, uint32_t row1, const T *wvec, double *Out64, double *colsum64,
+                double *wsum64, int acc_double, cudaStream_t s) {
+    if (row1 <= row0) return;
+#define OC_GRAM(KP, TA, TB)                                                                        \
+    if (acc_double)                                                                                \
+        launch_gram<T, double, KP, TA, TB>(A, lda, Kc, B, ldb, row0, row1, wvec, Out64, colsum64,  \
+                                           wsum64, s);                                             \
+    else                                                                                           \
+        launch_gram<T, T, KP, TA, TB>(A, lda, Kc, B, ldb, row0, row1, wvec, Out64, colsum64,       \
+                                      wsum64, s)
+    switch (kp) {
+        case 4: OC_GRAM(4, 1, 4); break;
+        case 8: OC_GRAM(8, 1, 4); break;
+        case 16: OC_GRAM(16, 2, 4); break;
+        case 32: OC_GRAM(32, 4, 4); break;
+        case 64: OC_GRAM(64, 4, 8); break;
+        case 128: OC_GRAM(128, 4, 8); break;
+        default: throw Error(-6, "padded latent dimension must be 4..128");
+    }
+#undef OC_GRAM
+}
+
+template <typename T>
+void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp,
+             cudaStream_t s) {
+    if (!M) return;
+    switch (kp) {
+        case 4: launch_rowgemm<T, 4, 1, 4>(A, lda, Ka, B, C, M, s); break;
+        case 8: launch_rowgemm<T, 8, 1, 4>(A, lda, Ka, B, C, M, s); break;
+        case 16: launch_rowgemm<T, 16, 2, 4>(A, lda, Ka, B, C, M, s); break;
+        case 32: launch_rowgemm<T, 32, 4, 4>(A, lda, Ka, B, C, M, s); break;
+        case 64: launch_rowgemm<T, 64, 4, 8>(A, lda, Ka, B, C, M, s); break;
+        case 128: launch_rowgemm<T, 128, 4, 8>(A, lda, Ka, B, C, M, s); break;
+        default: throw Error(-6, "padded latent dimension must be 4..128");
+    }
+}
+
+template <typename T>
+void convert_from_f64(const double *src, T *dst, uint64_t n, cudaStream_t s) {
+    if (!n) return;
+    OC_LAUNCH((k_convert<T>), ew_blocks(n), kThreads, 0, s, src, dst, n);
+}
+
+template <typename T>
+void cg_init(T *G, const T *W, const T *freq, T lambda, T *R, T *V, T *S, uint64_t D, int kp,
+             SolveScalars *sc, cudaStream_t s) {
+    const uint64_t nvec = D * kp / 4;
+    if (!nvec) return;
+    OC_LAUNCH((k_cg_init<T>), ew_blocks(nvec), kThreads, 0, s, G, W, freq, lambda, R, V, S, nvec,
+              kp / 4, sc);
+}
+
+template <typename T>
+void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, const SolveScalars *sc, cudaStream_t s) {
+    if (!n) return;
+    OC_LAUNCH((k_cg_dir<T>), ew_blocks(n / 4), kThreads, 0, s, V, R, Hv, n / 4, it, sc);
+}
+
+template <typename T>
+void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, int it,
+                SolveScalars *sc, cudaStream_t s) {
+    const uint64_t nvec = D * kp / 4;
+    if (!nvec) return;
+    OC_LAUNCH((k_cg_reg_dot<T>), ew_blocks(nvec), kThreads, 0, s, Hv, V, freq, lambda, nvec, kp / 4,
+              it, sc);
+}
+
+template <typename T>
+void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc,
+             cudaStream_t s) {
+    if (!n) return;
+    OC_LAUNCH((k_cg_step<T>), ew_blocks(n / 4), kThreads, 0, s, S, R, V, Hv, n / 4, it, sc);
+}
+
+template <typename T>
+void axpy(T *y, const T *x, T alpha, uint64_t n, cudaStream_t s) {
+    if (!n) return;
+    OC_LAUNCH((k_axpy<T>), ew_blocks(n / 4), kThreads, 0, s, y, x, alpha, n / 4);
+}
+
+template <typename T>
+void reduce_sum(const T *x, uint64_t n, int square, double *out64, cudaStream_t s) {
+    if (!n) return;
+    OC_LAUNCH((k_reduce_sum<T>), ew_blocks(n), kThreads, 0, s, x, n, square, out64);
+}
+
+template <typename T>
+void col_sums(const T *A, uint32_t lda, uint32_t cols, uint32_t row0, uint32_t row1, double *out64,
+              cudaStream_t s) {
+    if (row1 <= row0 || !cols) return;
+    const uint64_t rows = row1 - row0;
+    const uint64_t slabs = std::max<uint64_t>(1, std::min<uint64_t>((rows + 255) / 256, 2 * kSMs));
+    const uint32_t per = uint32_t((rows + slabs - 1) / slabs);
+    OC_LAUNCH((k_col_sums<T>), unsigned((rows + per - 1) / per), kThreads, 0, s, A, lda, cols, row0,
+              row1, out64, per);
+}
+
+template <typename T>
+void matvec_rows(const T *A, uint32_t lda, uint32_t cols, uint32_t rows, const T *v, T *out,
+                 cudaStream_t s) {
+    if (!rows) return;
+    OC_LAUNCH((k_matvec_rows<T>), unsigned((uint64_t(rows) * 32 + kThreads - 1) / kThreads), kThreads,
+              0, s, A, lda, cols, rows, v, out);
+}
+
+template <typename T>
+void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStream_t s) {
+    if (!nnz) return;
+    OC_LAUNCH((k_omega_objective<T>), ew_blocks(nnz), kThreads, 0, s, yt, nnz, w, r, out64);
+}
+
+#define OC_INSTANTIATE(T)                                                                           \
+    template void gram_stack<T>(const T *, uint32_t, uint32_t, const T *, uint32_t, int, uint32_t,  \
+                                uint32_t, const T *, double *, double *, double *, int,            \
+                                cudaStream_t);                                                      \
+    template void rowgemm<T>(const T *, uint32_t, uint32_t, const T *, T *, uint64_t, int,          \
+                             cudaStream_t);                                                         \
+    template void convert_from_f64<T>(const double *, T *, uint64_t, cudaStream_t);                 \
+    template void cg_init<T>(T *, const T *, const T *, T, T *, T *, T *, uint64_t, int,            \
+                             SolveScalars *, cudaStream_t);                                         \
+    template void cg_dir<T>(T *, const T *, T *, uint64_t, int, const SolveScalars *, cudaStream_t); \
+    template void cg_reg_dot<T>(T *, const T *, const T *, T, uint64_t, int, int, SolveScalars *,   \
+                                cudaStream_t);                                                      \
+    template void cg_step<T>(T *, T *, const T *, const T *, uint64_t, int, SolveScalars *,         \
+                             cudaStream_t);                                                         \
+    template void axpy<T>(T *, const T *, T, uint64_t, cudaStream_t);                               \
+    template void reduce_sum<T>(const T *, uint64_t, int, double *, cudaStream_t);                  \
+    template void col_sums<T>(const T *, uint32_t, uint32_t, uint32_t, uint32_t, double *,          \
+                              cudaStream_t);                                                        \
+    template void matvec_rows<T>(const T *, uint32_t, uint32_t, uint32_t, const T *, T *,           \
+                                 cudaStream_t);                                                     \
+    template void omega_objective<T>(const T *, uint64_t, T, T, double *, cudaStream_t);
+
+OC_INSTANTIATE(float)
+OC_INSTANTIATE(double)
+
+}  // namespace ocffm

@@ -1,0 +1,161 @@
+// kernels.h -- launcher prototypes of the sm_100a kernels (defined in rows.cu, dense.cu, eval.cu).
+// Every launcher is templated on the device real type T (float or double, explicitly
+// instantiated) and enqueues on the given stream without synchronising.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace ocffm {
+
+// One sparse design matrix X^phi (ImpData::Xs[phi], ffm.cpp:185-257) as SoA CSR on the device.
+template <typename T>
+struct CsrView {
+    const uint32_t *rowptr;  // [rows+1]
+    const uint32_t *idx;     // [nnz]
+    const T *val;            // [nnz]
+    uint32_t row0, row1;     // rows owned by this rank (global row ids)
+};
+
+// The observed pairs Omega in one orientation (U->Y by user or V->Y by item) cut into bounded
+// work items so that power-law rows cannot serialise a warp: item w covers nnz
+// [beg[w], beg[w] + (cnt[w] & 0x7fffffff)) of row row[w]; bit 31 of cnt marks the first chunk
+// of its row (the one that adds the row's non-Omega terms exactly once).
+template <typename T>
+struct OmegaView {
+    const uint32_t *wi_row, *wi_beg, *wi_cnt;
+    uint32_t n_items;
+    const uint32_t *rowptr;  // [rows+1] (global)
+    const uint32_t *idx;     // [nnz] column ids (items for the user orientation, users for the item one)
+    T *yt;                   // [nnz] y-tilde cache (Node::val of Y, ffm.cpp:393,400)
+    uint32_t row0, row1;     // rows owned by this rank
+    uint64_t nnz_local;
+};
+
+struct SolveScalars {       // device-resident fp64 scalars of one CG solve (ffm.cpp:761-811)
+    double r2[24];          // r2[it] = ||R||^2 before iteration it; r2[0] = g2 = ||G||^2
+    double vHv[24];
+    double bsum;            // sum(b1) of gd_side (ffm.cpp:551)
+    double misc[8];
+    double partials[148 * 8];   // per-block partial sums of the deterministic reductions
+    unsigned counter[4];
+};
+
+// ---- rows.cu ---------------------------------------------------------------------------------
+// C[i, 0:kp] = X_i * A   (UTX, ffm.cpp:314-331); C has leading dimension ldc
+template <typename T>
+void spmm_rows(const CsrView<T> &X, const T *A, T *C, uint32_t ldc, int kp, cudaStream_t s);
+
+// XS = X S ; P1 += XS ; side blocks also gap_i = XS_i . Q1_i, a1_i += gap_i
+// (update_side / update_cross, ffm.cpp:405-422, 439-449)
+template <typename T>
+void spmm_update(const CsrView<T> &X, const T *S, T *XS, T *P1, uint32_t ldp, const T *Q1side,
+                 T *gap, T *a1, int kp, cudaStream_t s);
+
+// gd_cross row pass (ffm.cpp:678-700): scatters X_i^T (pk_i + w (T_i + (a_i - r) oQ + bQ)) into G
+template <typename T>
+void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
+                     const T *Tm, const T *a1, const T *oQ, const T *bQ, T w, T r, T *G, int kp,
+                     cudaStream_t s);
+
+// hs_cross row pass (ffm.cpp:715-738): phi = X_i V, tau = X_i (V QTQ), ka = sum_j (phi.q_j) q_j
+template <typename T>
+void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
+                     const T *V, const T *VQ, T w, T *Hv, int kp, cudaStream_t s);
+
+// ysum[row] = sum of y-tilde over the row (first half of gd_side's z_i, ffm.cpp:577-580)
+template <typename T>
+void ytilde_rowsum(const OmegaView<T> &Y, T *ysum, int kp, cudaStream_t s);
+
+// gd_side (mode 0, ffm.cpp:572-589) / hs_side (mode 1, ffm.cpp:603-624) row pass
+template <typename T>
+void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, const T *a1,
+               const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
+               int kp, cudaStream_t s);
+
+// y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
+template <typename T>
+void sddmm_add(const OmegaView<T> &Y, const T *Uown, uint32_t ldu, const T *Vo, uint32_t ldv,
+               int kp, cudaStream_t s);
+
+// y-tilde[t] = a[row] + b[idx[t]] - 1  (base of init_y_tilde, ffm.cpp:393)
+template <typename T>
+void ytilde_base(const OmegaView<T> &Y, const T *a_own, const T *b_oth, cudaStream_t s);
+
+// y-tilde[t] += gap[row]  (own orientation) / += gap[idx[t]] (other orientation) (ffm.cpp:423-436)
+template <typename T>
+void ytilde_add_gap(const OmegaView<T> &Y, const T *gap, int by_row, cudaStream_t s);
+
+// out[i] (+)= sum_d P[i,d] Q[i,d]  (add_side, ffm.cpp:352-358)
+template <typename T>
+void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accumulate,
+                 cudaStream_t s);
+
+// ---- dense.cu --------------------------------------------------------------------------------
+// Out64[Kc x kp] += A[rows x Kc]^T B[rows x kp]; colsum64[0:kp] += B^T 1 ; wsum64[0:kp] += B^T wvec
+// (mm(a,b,c,k,l) ffm.cpp:41-45 for all cross pairs at once + mv ffm.cpp:660-661)
+template <typename T>
+void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, int kp,
+                uint32_t row0, uint32_t row1, const T *wvec, double *Out64, double *colsum64,
+                double *wsum64, int acc_double, cudaStream_t s);
+
+// C[M x kp] = A[M x Ka] B[Ka x kp]   (T = P~ Gstack, ffm.cpp:663-670; VQTQ = V QTQ, ffm.cpp:799)
+template <typename T>
+void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp,
+             cudaStream_t s);
+
+template <typename T>
+void convert_from_f64(const double *src, T *dst, uint64_t n, cudaStream_t s);
+
+// G += lambda * (freq ? freq[row] : 1) * W ; R = -G ; V = R ; S = 0 ; sc->r2[0] += ||G||^2
+template <typename T>
+void cg_init(T *G, const T *W, const T *freq, T lambda, T *R, T *V, T *S, uint64_t D, int kp,
+             SolveScalars *sc, cudaStream_t s);
+// it > 0: V = R + (r2[it]/r2[it-1]) V ; always Hv = 0
+template <typename T>
+void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, const SolveScalars *sc, cudaStream_t s);
+// Hv += lambda * (freq ? freq[row] : 1) * V ; sc->vHv[it] += V . Hv
+template <typename T>
+void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, int it,
+                SolveScalars *sc, cudaStream_t s);
+// alpha = r2[it]/vHv[it] ; S += alpha V ; R -= alpha Hv ; sc->r2[it+1] += ||R||^2
+template <typename T>
+void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc,
+             cudaStream_t s);
+template <typename T>
+void axpy(T *y, const T *x, T alpha, uint64_t n, cudaStream_t s);
+// out64 += sum(x) / sum(x*x) / colsum of a [rows x ld] matrix
+template <typename T>
+void reduce_sum(const T *x, uint64_t n, int square, double *out64, cudaStream_t s);
+template <typename T>
+void col_sums(const T *A, uint32_t lda, uint32_t cols, uint32_t row0, uint32_t row1, double *out64,
+              cudaStream_t s);
+// out[i] (+)= A[i, 0:cols] . v   (cache_sasb second mv, ffm.cpp:528,532)
+template <typename T>
+void matvec_rows(const T *A, uint32_t lda, uint32_t cols, uint32_t rows, const T *v, T *out,
+                 cudaStream_t s);
+// sum over Omega of (yt^2 - w (yt + 1 - r)^2) into out64 (objective, ffm.cpp:1338-1341 regrouped)
+template <typename T>
+void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStream_t s);
+
+// ---- eval.cu ---------------------------------------------------------------------------------
+// Fused full-ranking scorer + top-80 (pred_z ffm.cpp:915-923 + the argmax loops of prec_k / ndcg,
+// ffm.cpp:1029-1046, 1074-1108): for test rows [row0,row1) scores z = bt + P~va_i . Q~va_j over
+// items [0, n_ranked) are produced tile by tile in shared memory and never written to HBM;
+// ids[row*80 + rank] gets the 80 best (first index wins ties), UINT32_MAX padded.
+template <typename T>
+void score_topk(const T *Pva, const T *Qva, uint32_t Kc, const T *bt, uint32_t row0, uint32_t row1,
+                uint32_t n_ranked, const uint8_t *cold, uint32_t *ids, cudaStream_t s);
+// top-80 of a plain score vector (the `popular` ranking shared by all cold rows)
+template <typename T>
+void vector_topk(const T *z, uint32_t n_ranked, uint32_t *ids80, cudaStream_t s);
+// hits / dcg / idcg per row from the top-80 ids and the test labels, summed into acc64[0:5]
+// (hits@K), acc64[5:10] (sum of dcg/idcg @K); plus ploss sum in acc64[10] (ffm.cpp:982-986)
+template <typename T>
+void eval_metrics(const uint32_t *ids, const uint32_t *cold_ids80, const uint8_t *cold,
+                  const uint32_t *lab_rowptr, const uint32_t *lab_idx, uint32_t row0, uint32_t row1,
+                  const T *Pva, const T *Qva, uint32_t Kc, const T *at, const T *bt,
+                  const T *popular, uint32_t n_items, uint32_t n_ranked, double *acc64,
+                  cudaStream_t s);
+
+}  // namespace ocffm

@@ -1,0 +1,419 @@
+// rows.cu -- row-parallel sparse kernels of the solver (north_star subsystems 1 and 3).
+//
+// Mapping shared by every kernel here: the latent dimension is padded to kp = 4*G (G a power of
+// two <= 32) and a *lane group* of G consecutive lanes owns one row (or one bounded chunk of a
+// row of Omega); each lane keeps 4 consecutive latent components in registers, so one group
+// reads or writes a k-wide embedding row with one fully coalesced 16-byte (fp32) access per lane
+// and a warp works on 32/G rows at once.  Dots over k are group shuffles; X^T(.) scatters are
+// 16-byte REDs (red.global.add.v4.f32 on sm_100a) so no thread-private D x k scratch exists
+// (the reference's G_/Hv_ buffers, ffm.cpp:555-557, 672-674, 759).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ocffm {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int G>
+__device__ __forceinline__ uint32_t group_mask() {
+    if constexpr (G == 32) {
+        return 0xffffffffu;
+    } else {
+        const uint32_t lane = threadIdx.x & 31u;
+        return ((1u << G) - 1u) << (lane & ~uint32_t(G - 1));
+    }
+}
+
+template <int G, typename T>
+__device__ __forceinline__ T gsum(T v, uint32_t mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ V4<T> scale4(const V4<T> &v, T s) {
+    return {v.x * s, v.y * s, v.z * s, v.w * s};
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_spmm_rows(CsrView<T> X, const T *__restrict__ A, T *__restrict__ C, uint32_t ldc) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    const uint32_t lg = threadIdx.x % G;
+    if (g >= uint64_t(X.row1 - X.row0)) return;
+    const uint32_t row = X.row0 + uint32_t(g);
+    V4<T> acc = zero4<T>();
+    const uint32_t e = X.rowptr[row + 1];
+    for (uint32_t t = X.rowptr[row]; t < e; ++t)
+        fma4(acc, X.val[t], ldg4(A + size_t(X.idx[t]) * kp + lg * 4));
+    st4(C + size_t(row) * ldc + lg * 4, acc);
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_spmm_update(CsrView<T> X, const T *__restrict__ S, T *__restrict__ XS, T *__restrict__ P1,
+              uint32_t ldp, const T *__restrict__ Q1side, T *__restrict__ gap, T *__restrict__ a1) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    const uint32_t lg = threadIdx.x % G;
+    if (g >= uint64_t(X.row1 - X.row0)) return;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = X.row0 + uint32_t(g);
+    V4<T> acc = zero4<T>();
+    const uint32_t e = X.rowptr[row + 1];
+    for (uint32_t t = X.rowptr[row]; t < e; ++t)
+        fma4(acc, X.val[t], ldg4(S + size_t(X.idx[t]) * kp + lg * 4));
+    st4(XS + size_t(row) * kp + lg * 4, acc);
+    T *p = P1 + size_t(row) * ldp + lg * 4;
+    V4<T> pv = ld4(p);
+    pv.x += acc.x; pv.y += acc.y; pv.z += acc.z; pv.w += acc.w;
+    st4(p, pv);
+    if (Q1side) {
+        const T d = gsum<G>(dot4(acc, ldg4(Q1side + size_t(row) * kp + lg * 4)), mask);
+        if (lg == 0) {
+            gap[row] = d;
+            a1[row] += d;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
+             const T *__restrict__ Tm, const T *__restrict__ a1, const T *__restrict__ oQ,
+             const T *__restrict__ bQ, T w, T r, T *__restrict__ Gout) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= Y.n_items) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
+    const uint32_t cnt = c & 0x7fffffffu;
+    const bool first = (c >> 31) != 0;
+    const T omw = T(1) - w, cst = w * (T(1) - r);
+    V4<T> pk = zero4<T>();
+    for (uint32_t base = 0; base < cnt; base += G) {
+        const bool ok = base + lg < cnt;
+        const uint32_t t = beg + base + lg;
+        const uint32_t j = ok ? Y.idx[t] : 0u;
+        const T sc = ok ? omw * Y.yt[t] - cst : T(0);
+        const int nstep = min(int(G), int(cnt - base));
+#pragma unroll 4
+        for (int l = 0; l < nstep; ++l) {
+            const uint32_t jj = __shfl_sync(mask, j, l, G);
+            const T s = __shfl_sync(mask, sc, l, G);
+            fma4(pk, s, ldg4(Q1 + size_t(jj) * ldq + lg * 4));
+        }
+    }
+    if (first) {
+        const T zi = a1[row] - r;
+        const V4<T> t1 = ldg4(Tm + size_t(row) * kp + lg * 4);
+        const V4<T> o = ldg4(oQ + lg * 4), b = ldg4(bQ + lg * 4);
+        pk.x += w * (t1.x + zi * o.x + b.x);
+        pk.y += w * (t1.y + zi * o.y + b.y);
+        pk.z += w * (t1.z + zi * o.z + b.z);
+        pk.w += w * (t1.w + zi * o.w + b.w);
+    }
+    const uint32_t e = X.rowptr[row + 1];
+    for (uint32_t t = X.rowptr[row]; t < e; ++t)
+        red4(Gout + size_t(X.idx[t]) * kp + lg * 4, scale4(pk, X.val[t]));
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
+             const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= Y.n_items) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
+    const uint32_t cnt = c & 0x7fffffffu;
+    const bool first = (c >> 31) != 0;
+    const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
+    V4<T> phi = zero4<T>(), tau = zero4<T>();
+    for (uint32_t t = xb; t < xe; ++t) {
+        const size_t off = size_t(X.idx[t]) * kp + lg * 4;
+        const T v = X.val[t];
+        fma4(phi, v, ldg4(V + off));
+        if (first) fma4(tau, v, ldg4(VQ + off));
+    }
+    V4<T> ka = zero4<T>();
+    for (uint32_t base = 0; base < cnt; base += G) {
+        const bool ok = base + lg < cnt;
+        const uint32_t j = ok ? Y.idx[beg + base + lg] : 0u;
+        const int nstep = min(int(G), int(cnt - base));
+#pragma unroll 4
+        for (int l = 0; l < nstep; ++l) {
+            const uint32_t jj = __shfl_sync(mask, j, l, G);
+            const V4<T> q = ldg4(Q1 + size_t(jj) * ldq + lg * 4);
+            const T s = gsum<G>(dot4(phi, q), mask);
+            fma4(ka, s, q);
+        }
+    }
+    const T omw = T(1) - w;
+    V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
+               omw * ka.w + w * tau.w};
+    for (uint32_t t = xb; t < xe; ++t)
+        red4(Hv + size_t(X.idx[t]) * kp + lg * 4, scale4(z, X.val[t]));
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *__restrict__ Vo,
+            uint32_t ldv) {
+    const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= Y.n_items) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item];
+    const uint32_t cnt = Y.wi_cnt[item] & 0x7fffffffu;
+    if (cnt == 0) return;
+    const V4<T> u = ldg4(Uown + size_t(row) * ldu + lg * 4);
+    for (uint32_t base = 0; base < cnt; base += G) {
+        const bool ok = base + lg < cnt;
+        const uint32_t t = beg + base + lg;
+        const uint32_t j = ok ? Y.idx[t] : 0u;
+        const int nstep = min(int(G), int(cnt - base));
+        T mine = T(0);
+#pragma unroll 4
+        for (int l = 0; l < nstep; ++l) {
+            const uint32_t jj = __shfl_sync(mask, j, l, G);
+            const T s = gsum<G>(dot4(u, ldg4(Vo + size_t(jj) * ldv + lg * 4)), mask);
+            if (int(lg) == l) mine = s;
+        }
+        if (ok) Y.yt[t] += mine;
+    }
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_ytilde_rowsum(OmegaView<T> Y, T *__restrict__ ysum) {
+    const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= Y.n_items) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item];
+    const uint32_t cnt = Y.wi_cnt[item] & 0x7fffffffu;
+    T acc = T(0);
+    for (uint32_t o = lg; o < cnt; o += G) acc += Y.yt[beg + o];
+    acc = gsum<G>(acc, mask);
+    if (lg == 0 && cnt) atomicAdd(ysum + row, acc);
+}
+
+template <typename T, int G, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_side_rows(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, const T *__restrict__ a1,
+            const T *__restrict__ sa1, const T *__restrict__ ysum, const double *__restrict__ bsum,
+            const T *__restrict__ V, T w, T r, T n1, T *__restrict__ Out) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (g >= uint64_t(X.row1 - X.row0)) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = X.row0 + uint32_t(g);
+    const T cnt = T(Y.rowptr[row + 1] - Y.rowptr[row]);
+    const V4<T> q = ldg4(Q1 + size_t(row) * kp + lg * 4);
+    const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
+    T z;
+    if (MODE == 0) {
+        // z_i = w (n1 (a_i - r) + sum(b) + sa_i) + sum_Omega_i ((1-w) ytilde - w (1-r))
+        z = w * (n1 * (a1[row] - r) + T(*bsum) + sa1[row]) + (T(1) - w) * ysum[row] -
+            w * (T(1) - r) * cnt;
+    } else {
+        // d_i (q_i . X_i V),  d_i = (1-w) |Omega_i| + w n1
+        T acc = T(0);
+        for (uint32_t t = xb; t < xe; ++t)
+            acc += X.val[t] * dot4(q, ldg4(V + size_t(X.idx[t]) * kp + lg * 4));
+        z = gsum<G>(acc, mask) * ((T(1) - w) * cnt + w * n1);
+    }
+    for (uint32_t t = xb; t < xe; ++t)
+        red4(Out + size_t(X.idx[t]) * kp + lg * 4, scale4(q, X.val[t] * z));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_ytilde_base(OmegaView<T> Y, const T *__restrict__ a_own, const T *__restrict__ b_oth) {
+    constexpr int G = 8;
+    const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= Y.n_items) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item];
+    const uint32_t cnt = Y.wi_cnt[item] & 0x7fffffffu;
+    const T base = a_own[row] - T(1);
+    for (uint32_t o = lg; o < cnt; o += G) Y.yt[beg + o] = base + b_oth[Y.idx[beg + o]];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_ytilde_gap_by_row(OmegaView<T> Y, const T *__restrict__ gap) {
+    constexpr int G = 8;
+    const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= Y.n_items) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item];
+    const uint32_t cnt = Y.wi_cnt[item] & 0x7fffffffu;
+    const T g = gap[row];
+    for (uint32_t o = lg; o < cnt; o += G) Y.yt[beg + o] += g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_ytilde_gap_by_idx(OmegaView<T> Y, const T *__restrict__ gap) {
+    const uint64_t b = Y.rowptr[Y.row0], e = Y.rowptr[Y.row1];
+    for (uint64_t t = b + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < e;
+         t += uint64_t(gridDim.x) * blockDim.x)
+        Y.yt[t] += gap[Y.idx[t]];
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_rowwise_dot(const T *__restrict__ P, const T *__restrict__ Q, uint32_t rows, T *__restrict__ out,
+              int accumulate) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (g >= rows) return;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const T d = gsum<G>(dot4(ldg4(P + g * kp + lg * 4), ldg4(Q + g * kp + lg * 4)), mask);
+    if (lg == 0) out[g] = accumulate ? out[g] + d : d;
+}
+
+inline unsigned blocks_for(uint64_t groups, int G) {
+    const uint64_t threads = groups * uint64_t(G);
+    return unsigned((threads + kThreads - 1) / kThreads);
+}
+
+}  // namespace
+
+#define OC_DISPATCH_G(kp, ...)                                                      \
+    switch (kp) {                                                                   \
+        case 4: { constexpr int G = 1; __VA_ARGS__; } break;                        \
+        case 8: { constexpr int G = 2; __VA_ARGS__; } break;                        \
+        case 16: { constexpr int G = 4; __VA_ARGS__; } break;                       \
+        case 32: { constexpr int G = 8; __VA_ARGS__; } break;                       \
+        case 64: { constexpr int G = 16; __VA_ARGS__; } break;                      \
+        case 128: { constexpr int G = 32; __VA_ARGS__; } break;                     \
+        default: throw Error(-6, "padded latent dimension must be 4..128");         \
+    }
+
+template <typename T>
+void spmm_rows(const CsrView<T> &X, const T *A, T *C, uint32_t ldc, int kp, cudaStream_t s) {
+    const uint64_t rows = X.row1 - X.row0;
+    if (!rows) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_spmm_rows<T, G>), blocks_for(rows, G), kThreads, 0, s, X, A, C, ldc));
+}
+
+template <typename T>
+void spmm_update(const CsrView<T> &X, const T *S, T *XS, T *P1, uint32_t ldp, const T *Q1side,
+                 T *gap, T *a1, int kp, cudaStream_t s) {
+    const uint64_t rows = X.row1 - X.row0;
+    if (!rows) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_spmm_update<T, G>), blocks_for(rows, G), kThreads, 0, s, X, S, XS,
+                                P1, ldp, Q1side, gap, a1));
+}
+
+template <typename T>
+void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
+                     const T *Tm, const T *a1, const T *oQ, const T *bQ, T w, T r, T *G_, int kp,
+                     cudaStream_t s) {
+    if (!Y.n_items) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_grad_cross<T, G>), blocks_for(Y.n_items, G), kThreads, 0, s, Y, X,
+                                Q1, ldq, Tm, a1, oQ, bQ, w, r, G_));
+}
+
+template <typename T>
+void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
+                     const T *V, const T *VQ, T w, T *Hv, int kp, cudaStream_t s) {
+    if (!Y.n_items) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_hess_cross<T, G>), blocks_for(Y.n_items, G), kThreads, 0, s, Y, X,
+                                Q1, ldq, V, VQ, w, Hv));
+}
+
+template <typename T>
+void ytilde_rowsum(const OmegaView<T> &Y, T *ysum, int kp, cudaStream_t s) {
+    (void)kp;
+    if (!Y.n_items) return;
+    OC_LAUNCH((k_ytilde_rowsum<T, 8>), blocks_for(Y.n_items, 8), kThreads, 0, s, Y, ysum);
+}
+
+template <typename T>
+void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, const T *a1,
+               const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
+               int kp, cudaStream_t s) {
+    const uint64_t rows = X.row1 - X.row0;
+    if (!rows) return;
+    if (mode == 0) {
+        OC_DISPATCH_G(kp, OC_LAUNCH((k_side_rows<T, G, 0>), blocks_for(rows, G), kThreads, 0, s, Y, X,
+                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out));
+    } else {
+        OC_DISPATCH_G(kp, OC_LAUNCH((k_side_rows<T, G, 1>), blocks_for(rows, G), kThreads, 0, s, Y, X,
+                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out));
+    }
+}
+
+template <typename T>
+void sddmm_add(const OmegaView<T> &Y, const T *Uown, uint32_t ldu, const T *Vo, uint32_t ldv,
+               int kp, cudaStream_t s) {
+    if (!Y.n_items) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_sddmm_add<T, G>), blocks_for(Y.n_items, G), kThreads, 0, s, Y, Uown,
+                                ldu, Vo, ldv));
+}
+
+template <typename T>
+void ytilde_base(const OmegaView<T> &Y, const T *a_own, const T *b_oth, cudaStream_t s) {
+    if (!Y.n_items) return;
+    OC_LAUNCH((k_ytilde_base<T>), blocks_for(Y.n_items, 8), kThreads, 0, s, Y, a_own, b_oth);
+}
+
+template <typename T>
+void ytilde_add_gap(const OmegaView<T> &Y, const T *gap, int by_row, cudaStream_t s) {
+    if (by_row) {
+        if (!Y.n_items) return;
+        OC_LAUNCH((k_ytilde_gap_by_row<T>), blocks_for(Y.n_items, 8), kThreads, 0, s, Y, gap);
+    } else {
+        if (!Y.nnz_local) return;
+        const unsigned blocks = unsigned(std::min<uint64_t>((Y.nnz_local + kThreads - 1) / kThreads,
+                                                            uint64_t(kSMs) * 16));
+        OC_LAUNCH((k_ytilde_gap_by_idx<T>), blocks, kThreads, 0, s, Y, gap);
+    }
+}
+
+template <typename T>
+void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accumulate,
+                 cudaStream_t s) {
+    if (!rows) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_rowwise_dot<T, G>), blocks_for(rows, G), kThreads, 0, s, P, Q, rows,
+                                out, accumulate));
+}
+
+#define OC_INSTANTIATE(T)                                                                          \
+    template void spmm_rows<T>(const CsrView<T> &, const T *, T *, uint32_t, int, cudaStream_t);   \
+    template void spmm_update<T>(const CsrView<T> &, const T *, T *, T *, uint32_t, const T *, T *, \
+                                 T *, int, cudaStream_t);                                          \
+    template void grad_cross_rows<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, \
+                                     const T *, const T *, const T *, const T *, T, T, T *, int,   \
+                                     cudaStream_t);                                                \
+    template void hess_cross_rows<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, \
+                                     const T *, const T *, T, T *, int, cudaStream_t);             \
+    template void ytilde_rowsum<T>(const OmegaView<T> &, T *, int, cudaStream_t);                  \
+    template void side_rows<T>(int, const OmegaView<T> &, const CsrView<T> &, const T *, const T *, \
+                               const T *, const T *, const double *, const T *, T, T, T, T *, int, \
+                               cudaStream_t);                                                      \
+    template void sddmm_add<T>(const OmegaView<T> &, const T *, uint32_t, const T *, uint32_t, int, \
+                               cudaStream_t);                                                      \
+    template void ytilde_base<T>(const OmegaView<T> &, const T *, const T *, cudaStream_t);        \
+    template void ytilde_add_gap<T>(const OmegaView<T> &, const T *, int, cudaStream_t);           \
+    template void rowwise_dot<T>(const T *, const T *, uint32_t, int, T *, int, cudaStream_t);
+
+OC_INSTANTIATE(float)
+OC_INSTANTIATE(double)
+
+}  // namespace ocffm
