@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: sec per outer iteration and nnz/s at d=32
+on the KKBox-shaped synthetic set (BASELINE.json configs[1], SURVEY.md 8 shape C2), plus
+full-ranking eval users/s, measured through the C ABI of libocffm_cuda.so.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one outer iteration (one_epoch, ffm.cpp:852-870: every side + cross block solve and
+cache_sasb) over the whole synthetic set.  `value` = nnz/s = N_trav / time with N_trav as defined
+in SURVEY.md 8(d) (it normalises out CG-count differences), inputs resident in HBM; `e2e` = the
+same metric when every step starts from a HOST-resident model (H2D of all W/H, state rebuild,
+the epoch, D2H of all W/H).  `--impl reference` times the UNMODIFIED reference's own
+one_epoch()/validate() (oracle/_ref/ref_harness_blas, built from /root/reference by
+oracle/Makefile) on the box's host cores on a bounded sample of the same workload.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "one-class-ffm_b200"))
+
+HYPER = dict(lam=4.0, omega=2.0 ** -7, r=-1.0)     # script/grid.sh:237 canonical flags
+WORKLOADS = {
+    # name -> (shape, k, test rows)
+    "C2": ("C2", 32, 30_000),
+    "C1": ("C1", 16, 2_000),
+    "C3": ("C3", 16, 20_000),
+    "C4": ("C4", 32, 20_000),
+}
+CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.sm_max, reasons=sorted(self.reasons))
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.sm_max,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+def run_reference_arm(args, shape, k, test_rows):
+    """Times the unmodified reference (oracle/_ref) on host cores on a bounded sample."""
+    import synth
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness_blas")
+    kind = "reference"
+    if not os.path.exists(harness):
+        harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        return None
+    scale = args.cpu_scale or CPU_SAMPLE_SCALE[args.workload]
+    ds = synth.generate(shape, seed=args.seed, scale=scale, test_rows=max(64, int(test_rows * scale * 0.1)))
+    ncpu = os.cpu_count() or 1
+    threads = args.cpu_threads or min(ncpu, 16)
+    epochs = args.warmup + args.steps
+    with tempfile.TemporaryDirectory() as tmp:
+        item_p, tr_p, te_p = synth.write_text(ds, tmp)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads))
+        cmd = [harness, "time", item_p, tr_p, te_p, str(epochs), "-k", str(k), "-l", str(HYPER["lam"]),
+               "-w", str(HYPER["omega"]), "-r", str(HYPER["r"]), "-c", str(threads)]
+        t0 = time.time()
+        out = subprocess.check_output(cmd, env=env, text=True)
+        wall = time.time() - t0
+    res = json.loads(out.strip().splitlines()[-1])
+    ep = res["epochs"][args.warmup:]
+    nnz_y = int(ds.train.idx.size)
+    fu, fv = ds.users.f, ds.items.f
+    nnzx_u = [int(f.idx.size) for f in ds.users.fields]
+    nnzx_v = [int(f.idx.size) for f in ds.items.fields]
+    # per-block CG counts in one_epoch order (harness prints them); N_trav per SURVEY.md 8(d) with
+    # a block's CG iterations split evenly between its two halves for the (small) nnzX term
+    n_trav = 0.0
+    for e in ep:
+        for blk in e["blocks"]:
+            f1, f2, c = blk["f1"], blk["f2"], blk["cg"]
+            xa = nnzx_u[f1] if f1 < fu else nnzx_v[f1 - fu]
+            xb = nnzx_u[f2] if f2 < fu else nnzx_v[f2 - fu]
+            cross = f1 < fu <= f2
+            n_trav += 2 * nnz_y + xa + xb                       # two gradients
+            n_trav += c * ((nnz_y if cross else 0) + (xa + xb) / 2.0)
+            n_trav += 2 * (2 * nnz_y) + xa + xb                 # two updates
+    sec = sum(e["sec"] for e in ep)
+    value = n_trav / sec
+    sample = (f"{shape} scaled x{scale} (m={ds.m}, n={ds.n}, nnz_y={nnz_y}), k={k}, {len(ep)} timed epochs "
+              f"after {args.warmup} warm-up, {threads} OpenMP threads, OpenBLAS pinned to 1 thread")
+    return dict(kind=kind, value=value, sec_per_epoch=sec / len(ep), cores=threads, host_cores=ncpu,
+                sample=sample, cg_iters=[e["cg_iters"] for e in ep], wall_s=wall,
+                eval_users_per_s=(res["m_t"] / res["validate_s"]) if "validate_s" in res else None,
+                harness=os.path.basename(harness))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--ns", action="store_true", help="--ns: cross blocks only")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only)")
+    ap.add_argument("--cpu-scale", type=float, default=0.0)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    shape, k, test_rows = WORKLOADS[args.workload]
+    config = dict(workload=f"{args.workload}: KKBox-shaped synthetic one-class set" if args.workload == "C2"
+                  else f"{args.workload} synthetic one-class set",
+                  shape=shape, k=k, lam=HYPER["lam"], omega=HYPER["omega"], r=HYPER["r"],
+                  self_side=not args.ns, seed=args.seed, zipf=1.3, l2="inputs larger than L2 (126 MB)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ref = run_reference_arm(args, shape, k, test_rows)
+        if ref is None:
+            print(json.dumps(dict(impl="reference", unavailable="oracle/_ref binaries missing (make -C oracle ref)")))
+            return
+        config.update(sample=ref["sample"])
+        line = dict(metric="nnz_per_s", value=ref["value"], unit="nnz/s", n_gpus=0, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=1e3 * ref["sec_per_epoch"], higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                    impl="reference", sec_per_outer_iteration=ref["sec_per_epoch"],
+                    eval_users_per_s=ref["eval_users_per_s"], gpu_launches=0,
+                    cpu_baseline=dict(value=ref["value"], unit="nnz/s", cores=ref["cores"], kind=ref["kind"],
+                                      sample=ref["sample"]),
+                    e2e=dict(value=ref["value"], unit="nnz/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ocffm
+    import synth
+
+    if ocffm.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; libocffm_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        box = [ocffm.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = (world, rank, box[0])
+
+    t_gen = time.time()
+    gen_kw = dict(shape=shape, seed=args.seed, scale=args.scale,
+                  test_rows=0 if args.no_eval else max(64, int(test_rows * args.scale)))
+    if world > 1:
+        # one rank generates, the others read its pickle (the generator is seeded, this only saves time)
+        import pickle
+        cache = os.path.join(tempfile.gettempdir(), f"ocffm_{shape}_{args.seed}_{args.scale}_{gen_kw['test_rows']}.pkl")
+        if rank == 0:
+            ds = synth.generate(**gen_kw)
+            with open(cache + ".tmp", "wb") as fh:
+                pickle.dump(ds, fh, protocol=4)
+            os.replace(cache + ".tmp", cache)
+        dist.barrier()
+        if rank != 0:
+            with open(cache, "rb") as fh:
+                ds = pickle.load(fh)
+    else:
+        ds = synth.generate(**gen_kw)
+    t_gen = time.time() - t_gen
+    config.update(m=ds.m, n=ds.n, nnz_y=int(ds.train.idx.size), fu=ds.users.f, fv=ds.items.f,
+                  m_t=0 if ds.test is None else ds.test.rows, parallelism=f"rows sharded over {world} GPU(s)")
+    dtype = ocffm.F32 if args.dtype == "f32" else ocffm.F64
+    os.environ.setdefault("OCFFM_PROFILE", "1")     # CUDA events around every hv_cross launch
+    prob = ocffm.Problem(ds, k=k, dtype=dtype, device=local_rank, self_side=not args.ns, comm=comm, **HYPER)
+    model = prob.init_model(seed=args.seed)
+    prob.init_state()
+    stream = torch.cuda.ExternalStream(prob.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        prob.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        prob.one_epoch()
+    barrier()
+    prob.reset_stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        prob.one_epoch()
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    st = prob.stats()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sec = ms / 1e3
+    value = st.nnz_traversed / sec
+    objective = prob.objective()
+
+    pk = peaks()
+    hv_gbs = (st.hv_algo_bytes / 1e9) / (st.hv_ms / 1e3) if st.hv_ms > 0 else None
+    roofline = dict(bound="hbm", kernel="k_hess_cross (hs_cross row pass)", achieved=hv_gbs, peak=pk["hbm_gbs"],
+                    unit="GB/s", frac=(hv_gbs / pk["hbm_gbs"]) if hv_gbs else None, traffic=None,
+                    peak_source=pk["source"], launches=int(st.hv_launches),
+                    avg_launch_ms=(st.hv_ms / st.hv_launches) if st.hv_launches else None,
+                    share_of_step=(st.hv_ms / ms) if ms > 0 else None,
+                    algo_bytes_per_launch=(st.hv_algo_bytes / st.hv_launches) if st.hv_launches else None,
+                    whole_epoch_gbs=(st.algo_bytes / 1e9) / sec)
+
+    # ---- evaluation (validate, ffm.cpp:925-1016) --------------------------------------------
+    eval_info = None
+    if ds.test is not None:
+        prob.validate(want_topk=False)          # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = prob.validate(want_topk=False)
+        e1.record(stream)
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        fx = ds.users.f * ds.items.f
+        flops = 2.0 * ds.test.rows * ds.train.n_items * fx * k
+        eval_info = dict(users_per_s=ds.test.rows / (ems / 1e3), ms=ems, m_t=ds.test.rows,
+                         n_ranked=ds.train.n_items, tflops=flops / (ems / 1e3) / 1e12,
+                         p_at_10=float(res["prec"][1]), ndcg_at_10=float(res["ndcg"][1]), ploss=float(res["ploss"]))
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------
+    e2e_steps = min(args.steps, 3)
+    host_model = {key: np.ascontiguousarray(prob.get_block(*key)) for key in model}
+    bytes_model = int(sum(v.nbytes for v in host_model.values()))
+    barrier()
+    prob.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for key, w in host_model.items():
+            prob.set_block(key[0], key[1], key[2], w)      # H2D
+        prob.init_state()
+        prob.one_epoch()
+        for key in host_model:
+            host_model[key] = prob.get_block(*key)         # D2H
+    prob.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    st2 = prob.stats()
+    e2e = dict(value=st2.nnz_traversed / e2e_sec, unit="nnz/s", h2d_bytes_per_step=bytes_model,
+               d2h_bytes_per_step=bytes_model, steps=e2e_steps, sec_per_step=e2e_sec / e2e_steps,
+               what="per step: ocffm_set_block for every W/H (H2D), ocffm_init_state, ocffm_one_epoch, "
+                    "ocffm_get_block for every W/H (D2H)")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            ref_args = argparse.Namespace(**vars(args))
+            ref_args.steps, ref_args.warmup = 2, 1
+            r = run_reference_arm(ref_args, shape, k, test_rows)
+            if r:
+                cpu = dict(value=r["value"], unit="nnz/s", cores=r["cores"], kind=r["kind"], sample=r["sample"],
+                           sec_per_epoch=r["sec_per_epoch"], eval_users_per_s=r["eval_users_per_s"],
+                           host_cores=r["host_cores"])
+        except Exception as exc:  # the baseline is reported, never required
+            cpu = dict(value=None, unit="nnz/s", cores=0, kind="reference", sample=f"failed: {exc}")
+
+    if rank == 0:
+        line = dict(metric="nnz_per_s", value=value, unit="nnz/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling="strong", vs_baseline=None, dtype=args.dtype, data="synthetic", config=config,
+                    sec_per_outer_iteration=sec / args.steps, cg_iters_per_step=st.cg_iters / args.steps,
+                    objective=objective, gpu_launches=int(st.kernel_launches), e2e=e2e, roofline=roofline,
+                    cpu_baseline=cpu, eval=eval_info, clocks=sampler.summary(), datagen_s=t_gen)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,11 +124,24 @@ def _gen_field(rng: np.random.Generator, rows: int, spec: FieldSpec) -> Field:
 def _gen_labels(rng: np.random.Generator, rows: int, n_items: int, pos: float, zipf: float,
                 perm: np.ndarray, min_pos: int = 0) -> Labels:
     cnt = np.maximum(rng.poisson(pos, size=rows), min_pos).astype(np.int64)
-    tot = int(cnt.sum())
+    cnt = np.minimum(cnt, n_items)
     cdf = _zipf_cdf(n_items, zipf)
+    # Heavy users would lose most of their Zipf draws to duplicates: oversample, de-duplicate,
+    # then keep a uniformly random `cnt` of each user's distinct items.
+    over = 6 if pos > 20 else 1
+    draws = cnt * over
+    tot = int(draws.sum())
     items = perm[np.searchsorted(cdf, rng.random(tot))].astype(np.int64)
-    users = np.repeat(np.arange(rows, dtype=np.int64), cnt)
+    users = np.repeat(np.arange(rows, dtype=np.int64), draws)
     key = np.unique(users * n_items + items)          # de-duplicate, sort by (user, item)
+    if over > 1:
+        users = key // n_items
+        prio = rng.random(key.size)
+        order = np.lexsort((prio, users))
+        start = np.zeros(rows + 1, dtype=np.int64)
+        start[1:] = np.cumsum(np.bincount(users, minlength=rows))
+        rank_in_user = np.arange(key.size, dtype=np.int64) - start[users[order]]
+        key = np.sort(key[order[rank_in_user < cnt[users[order]]]])
     users, items = key // n_items, key % n_items
     rowptr = np.zeros(rows + 1, dtype=np.uint64)
     rowptr[1:] = np.cumsum(np.bincount(users, minlength=rows))

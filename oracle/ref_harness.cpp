@@ -234,12 +234,32 @@ int main(int argc, char **argv) {
                U->m, V->m, U->nnz_y, a.param->nr_threads,
                chrono::duration<double>(t1 - t0).count(), chrono::duration<double>(t2 - t1).count());
         for (int e = 0; e < epochs; e++) {
+            // one_epoch()'s own block order (ffm.cpp:852-870), block by block through the
+            // reference's solve_side / solve_cross / cache_sasb so that per-block CG counts
+            // (needed for N_trav) can be read off the shim counter
             const long c0 = ocffm_shim_dscal_calls;
+            string blocks;
             auto s = chrono::steady_clock::now();
-            prob.one_epoch();
+            auto run = [&](ImpInt f1, ImpInt f2, bool side) {
+                const long b0 = ocffm_shim_dscal_calls;
+                if (side) prob.solve_side(f1, f2);
+                else prob.solve_cross(f1, f2);
+                blocks += (blocks.empty() ? "" : ", ") + string("{\"f1\": ") + to_string(f1) + ", \"f2\": " +
+                          to_string(f2) + ", \"cg\": " + to_string(ocffm_shim_dscal_calls - b0) + "}";
+            };
+            const ImpInt fu = prob.fu, f = prob.f;
+            if (a.param->self_side) {
+                for (ImpInt f1 = 0; f1 < fu; f1++)
+                    for (ImpInt f2 = f1; f2 < fu; f2++) run(f1, f2, true);
+                for (ImpInt f1 = fu; f1 < f; f1++)
+                    for (ImpInt f2 = f1; f2 < f; f2++) run(f1, f2, true);
+            }
+            for (ImpInt f1 = 0; f1 < fu; f1++)
+                for (ImpInt f2 = fu; f2 < f; f2++) run(f1, f2, false);
+            if (a.param->self_side) prob.cache_sasb();
             auto t = chrono::steady_clock::now();
-            printf("%s{\"sec\": %.6f, \"cg_iters\": %ld}", e ? ", " : "",
-                   chrono::duration<double>(t - s).count(), ocffm_shim_dscal_calls - c0);
+            printf("%s{\"sec\": %.6f, \"cg_iters\": %ld, \"blocks\": [%s]}", e ? ", " : "",
+                   chrono::duration<double>(t - s).count(), ocffm_shim_dscal_calls - c0, blocks.c_str());
             fflush(stdout);
         }
         printf("]");
