@@ -197,7 +197,9 @@ struct Problem final : CtxBase {
 
     std::vector<Field> XU, XV, XT;
     Omega YU, YV;
-    DevBuf<uint32_t> t_rowptr, t_idx, topk_ids, cold_ids;
+    DevBuf<uint32_t> t_rowptr, t_idx, topk_ids, cold_ids, part_id;
+    DevBuf<T> part_score;
+    bool cold_ready = false;
     DevBuf<uint8_t> t_cold;
     std::vector<uint8_t> h_cold;
     bool test_set = false;
@@ -213,6 +215,10 @@ struct Problem final : CtxBase {
     DevBuf<double> gram64, acc64;
     SolveScalars *sc = nullptr;
     double *h_scal = nullptr;  // pinned
+    double *h_stage = nullptr; // pinned staging for model blocks crossing the ABI as fp64
+    size_t h_stage_n = 0;
+    DevBuf<double> d_stage;
+    cudaEvent_t cg_ev[24];
 
     // stats
     uint64_t launches = 0, cg_iters = 0, nnz_trav = 0, algo_bytes = 0, hv_launches = 0,
@@ -234,6 +240,7 @@ struct Problem final : CtxBase {
         OC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         OC_CUDA(cudaMalloc(&sc, sizeof(SolveScalars)));
         OC_CUDA(cudaMallocHost(&h_scal, 64 * sizeof(double)));
+        for (auto &e : cg_ev) OC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         XU.resize(fu);
         XV.resize(fv);
         XT.resize(fu);
@@ -248,7 +255,7 @@ struct Problem final : CtxBase {
                 if (!bk.side) bk.pair = int(f1 * fv + (f2 - fu));
             }
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
-        if (const char *e = getenv("OCFFM_PROFILE")) profile = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
         a.zero(st); b.zero(st); sa.zero(st); sb.zero(st);
         Pc.alloc(m * Kc); Qc.alloc(n * Kc);
@@ -262,8 +269,10 @@ struct Problem final : CtxBase {
     ~Problem() override {
         cudaSetDevice(device);
         for (auto &e : hv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto &e : cg_ev) cudaEventDestroy(e);
         if (sc) cudaFree(sc);
         if (h_scal) cudaFreeHost(h_scal);
+        if (h_stage) cudaFreeHost(h_stage);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -387,6 +396,7 @@ struct Problem final : CtxBase {
         }
         std::vector<T> pv(h_popular.begin(), h_popular.end());
         popular.upload(pv, st);
+        cold_ready = false;
         // CSC by (item, user): transY (ffm.cpp:259-294); labels >= n are dropped there
         std::vector<uint64_t> colptr;
         std::vector<uint32_t> rowidx;
@@ -449,19 +459,31 @@ struct Problem final : CtxBase {
     uint64_t block_rows(const Block &bk, int which) {
         return which == 'W' ? field_of(bk.f1).D : field_of(bk.f2).D;
     }
+    void ensure_stage(size_t n_) {
+        if (n_ <= h_stage_n) return;
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        OC_CUDA(cudaMallocHost(&h_stage, n_ * sizeof(double)));
+        h_stage_n = n_;
+        d_stage.alloc(n_);
+    }
+    // fp64 [rows x k] host -> pinned staging -> device -> T [rows x kp] (conversion on the device)
     void upload_padded(DevBuf<T> &dst, const double *src, uint64_t rows) {
-        std::vector<T> h(rows * kp, T(0));
-        for (uint64_t i = 0; i < rows; ++i)
-            for (uint32_t d = 0; d < k; ++d) h[i * kp + d] = T(src[i * k + d]);
-        dst.upload(h, st);
+        const size_t cnt = rows * k;
+        ensure_stage(cnt);
+        memcpy(h_stage, src, cnt * sizeof(double));
+        OC_CUDA(cudaMemcpyAsync(d_stage.p, h_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        dst.ensure(rows * kp);
+        pad_from_f64<T>(d_stage.p, dst.p, rows, k, kp, st);
         sync();
     }
     void download_unpadded(const T *src, uint64_t ld, double *dst, uint64_t rows) {
-        std::vector<T> h(rows * ld);
-        OC_CUDA(cudaMemcpyAsync(h.data(), src, rows * ld * sizeof(T), cudaMemcpyDeviceToHost, st));
+        const size_t cnt = rows * k;
+        ensure_stage(cnt);
+        unpad_to_f64<T>(src, uint32_t(ld), d_stage.p, rows, k, st);
+        OC_CUDA(cudaMemcpyAsync(h_stage, d_stage.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         sync();
-        for (uint64_t i = 0; i < rows; ++i)
-            for (uint32_t d = 0; d < k; ++d) dst[i * k + d] = double(h[i * ld + d]);
+        memcpy(dst, h_stage, cnt * sizeof(double));
     }
     void set_block(uint32_t f1, uint32_t f2, int which, const double *data, uint64_t rows) override {
         OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
@@ -617,13 +639,13 @@ struct Problem final : CtxBase {
             OC_CUDA(cudaMemsetAsync(&sc->bsum, 0, sizeof(double), st));
             reduce_sum<T>(h.b1, h.n1, 0, &sc->bsum, st);
             side_rows<T>(0, h.Yown->view(), h.X->view(), h.Q1, h.a1, h.sa1, ysum.p, &sc->bsum, nullptr,
-                         T(prm.omega), T(prm.r), T(h.n1), G.p, kp, st);
+                         T(prm.omega), T(prm.r), T(h.n1), G.p, kp, kNoGate, st);
             algo_bytes += nnzY * s + h.m1 * (k + 3) * s + nnzX * (4 + s) + 2 * h.D * k * s;
         } else {
             prepare_cross(h);
             const T *Ps = h.user ? Pc.p : Qc.p;
             const uint32_t r0 = h.Yown->row0, r1 = h.Yown->row1;
-            rowgemm<T>(Ps + size_t(r0) * Kc, Kc, Kc, GT.p, Tm.p + size_t(r0) * kp, r1 - r0, kp, st);
+            rowgemm<T>(Ps + size_t(r0) * Kc, Kc, Kc, GT.p, Tm.p + size_t(r0) * kp, r1 - r0, kp, kNoGate, st);
             grad_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, Tm.p, h.a1, oQ.p, bQ.p,
                                T(prm.omega), T(prm.r), G.p, kp, st);
             algo_bytes += (h.m1 + 1) * 8 + nnzY * (4 + s) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
@@ -650,18 +672,14 @@ struct Problem final : CtxBase {
         hv_events_used = 0;
     }
 
-    // Hv (without the regulariser) for the direction in V; VQ must hold V QTQ for cross halves
-    void hess_scatter(const Half &h) {
-        const size_t s = sizeof(T);
-        const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+    // Hv (without the regulariser) for the direction in V.  Returns nothing; the caller accounts
+    // the statistics with account_hess() once it knows the iteration really ran.
+    void hess_scatter(const Half &h, Gate gate) {
         if (h.side) {
             side_rows<T>(1, h.Yown->view(), h.X->view(), h.Q1, nullptr, nullptr, nullptr, nullptr, V.p,
-                         T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, st);
-            algo_bytes += nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) + h.m1 * k * s +
-                          h.m1 * 4 + h.D * k * s;
-            nnz_trav += nnzX;
+                         T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, gate, st);
         } else {
-            rowgemm<T>(V.p, kp, kp, qtq_of(h), VQ.p, h.D, kp, st);
+            rowgemm<T>(V.p, kp, kp, qtq_of(h), VQ.p, h.D, kp, gate, st);
             size_t ev = 0;
             if (profile) {
                 if (hv_events_used >= 4096) { sync(); drain_hv_events(); }
@@ -669,17 +687,28 @@ struct Problem final : CtxBase {
                 OC_CUDA(cudaEventRecord(hv_events[ev].first, st));
             }
             hess_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega), Hv.p,
-                               kp, st);
+                               kp, gate, st);
             if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
+        }
+        comm.allreduce(Hv.p, h.D * kp, st);
+    }
+    void account_hess(const Half &h, uint64_t iters) {
+        const size_t s = sizeof(T);
+        const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        if (h.side) {
+            algo_bytes += iters * (nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) + h.m1 * k * s +
+                                   h.m1 * 4 + h.D * k * s);
+            nnz_trav += iters * nnzX;
+        } else {
             const uint64_t bytes = (h.m1 + 1) * 8 + nnzX * (4 + s) +
                                    gather_bytes(h.D * k * s, nnzX, k * s) + nnzY * 4 +
                                    gather_bytes(h.n1 * k * s, nnzY, k * s) + h.D * k * s;
-            algo_bytes += bytes;
-            hv_algo_bytes += bytes;
-            hv_launches++;
-            nnz_trav += nnzY + nnzX;
+            algo_bytes += iters * bytes;
+            hv_algo_bytes += iters * bytes;
+            hv_launches += iters;
+            nnz_trav += iters * (nnzY + nnzX);
         }
-        comm.allreduce(Hv.p, h.D * kp, st);
+        algo_bytes += iters * 7 * h.D * k * s;
     }
 
     double read_scalar(const double *dev) {
@@ -690,24 +719,37 @@ struct Problem final : CtxBase {
 
     // cg, ffm.cpp:744-813.  G holds the gradient WITHOUT lambda W when add_reg is set (solver
     // path, the regulariser is fused into cg_init), or the full gradient otherwise.
-    int run_cg(const Half &h, bool add_reg) {
+    // Iteration it+1 is enqueued before r2[it+1] has been read back; its kernels carry a device
+    // side gate that re-evaluates the reference's stop test (g2 * 0.09 < r2, ffm.cpp:780), so a
+    // speculative iteration past the stop is a no-op and the GPU never idles on the host.
+    void enqueue_cg_iter(const Half &h, int it) {
         const uint64_t len = h.D * kp;
+        cg_dir<T>(V.p, R.p, Hv.p, len, it, sc, st);
+        hess_scatter(h, Gate{sc, it});
+        cg_reg_dot<T>(Hv.p, V.p, h.freq, T(prm.lambda), h.D, kp, it, sc, 1, st);
+        cg_step<T>(S.p, R.p, V.p, Hv.p, len, it, sc, st);
+        OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
+        OC_CUDA(cudaEventRecord(cg_ev[it], st));
+    }
+    int run_cg(const Half &h, bool add_reg) {
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
         cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, st);
         const double g2 = read_scalar(&sc->r2[0]);
-        double r2 = g2;
-        int it = 0;
         const int max_cg = 20;
         const double eps = 9e-2;
-        while (g2 * eps < r2 && it < max_cg) {
-            cg_dir<T>(V.p, R.p, Hv.p, len, it, sc, st);
-            hess_scatter(h);
-            cg_reg_dot<T>(Hv.p, V.p, h.freq, T(prm.lambda), h.D, kp, it, sc, st);
-            cg_step<T>(S.p, R.p, V.p, Hv.p, len, it, sc, st);
-            algo_bytes += 7 * h.D * k * sizeof(T);
-            r2 = read_scalar(&sc->r2[it + 1]);
-            ++it;
+        int it = 0;
+        if (g2 * eps < g2) {
+            enqueue_cg_iter(h, 0);
+            for (;;) {
+                if (it + 1 < max_cg) enqueue_cg_iter(h, it + 1);   // speculative
+                OC_CUDA(cudaEventSynchronize(cg_ev[it]));
+                const double r2 = h_scal[1 + it];
+                ++it;
+                if (!(g2 * eps < r2) || it >= max_cg) break;
+            }
+            sync();   // the gated no-op iteration (if any) must drain before S is consumed elsewhere
         }
+        account_hess(h, uint64_t(it));
         cg_iters += uint64_t(it);
         return it;
     }
@@ -760,11 +802,42 @@ struct Problem final : CtxBase {
     void strided_add(T *dst, uint32_t ld, const T *src, uint64_t rows);
     void axpy_scalar_vec(T *y, const T *x, uint64_t n_);
 
+    // phase timers (OCFFM_PROFILE >= 2): events at the phase boundaries of every half solve
+    std::vector<cudaEvent_t> ph_events;
+    std::vector<int> ph_kind;   // 0 = side, 1 = cross
+    int profile_level = 0;
+    void phase_mark(int kind) {
+        if (profile_level < 2) return;
+        cudaEvent_t e;
+        OC_CUDA(cudaEventCreate(&e));
+        OC_CUDA(cudaEventRecord(e, st));
+        ph_events.push_back(e);
+        ph_kind.push_back(kind);
+    }
+    void drain_phases() {
+        // events come in groups of 4 per half solve: start, after grad, after cg, after update
+        for (size_t i = 0; i + 3 < ph_events.size(); i += 4) {
+            float g = 0, c = 0, u = 0;
+            cudaEventElapsedTime(&g, ph_events[i], ph_events[i + 1]);
+            cudaEventElapsedTime(&c, ph_events[i + 1], ph_events[i + 2]);
+            cudaEventElapsedTime(&u, ph_events[i + 2], ph_events[i + 3]);
+            const int o = ph_kind[i] ? 3 : 0;
+            ms[o + 0] += g; ms[o + 1] += c; ms[o + 2] += u;
+        }
+        for (auto e : ph_events) cudaEventDestroy(e);
+        ph_events.clear();
+        ph_kind.clear();
+    }
     void solve_half(uint32_t f1, uint32_t f2, int which) {
         Half h = half_of(f1, f2, which);
+        const int kind = h.side ? 0 : 1;
+        phase_mark(kind);
         grad_scatter(h);
+        phase_mark(kind);
         run_cg(h, true);
+        phase_mark(kind);
         apply_update(h);
+        phase_mark(kind);
     }
     void solve_block(uint32_t f1, uint32_t f2) override {
         solve_half(f1, f2, 'W');   // W first, then H against the updated P1 (ffm.cpp:826-832, 843-849)
@@ -782,7 +855,7 @@ struct Problem final : CtxBase {
             for (uint32_t f2 = fu; f2 < f; ++f2) solve_block(f1, f2);
         if (prm.self_side) cache_sasb();
         sync();
-        if (profile) drain_hv_events();
+        if (profile) { drain_hv_events(); drain_phases(); }
     }
 
     // ---- observation entry points (parity tests) -------------------------------------------------
@@ -793,7 +866,7 @@ struct Problem final : CtxBase {
             axpy<T>(dst, src, T(prm.lambda), h.D * kp, st);
         } else {
             OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
-            cg_reg_dot<T>(dst, src, h.freq, T(prm.lambda), h.D, kp, 0, sc, st);
+            cg_reg_dot<T>(dst, src, h.freq, T(prm.lambda), h.D, kp, 0, sc, 0, st);
         }
     }
     void grad(uint32_t f1, uint32_t f2, int which, double *Gout, uint64_t rows) override {
@@ -810,7 +883,7 @@ struct Problem final : CtxBase {
         upload_padded(V, Vin, h.D);
         if (!h.side) prepare_cross(h);
         OC_CUDA(cudaMemsetAsync(Hv.p, 0, h.D * kp * sizeof(T), st));
-        hess_scatter(h);
+        hess_scatter(h, kNoGate);
         add_reg_into(Hv.p, V.p, h);
         download_unpadded(Hv.p, kp, Hout, h.D);
     }
@@ -912,8 +985,15 @@ struct Problem final : CtxBase {
                 rowwise_dot<T>(t1.p, t2.p, uint32_t(n), kp, bt.p, 1, st);
             }
         }
-        vector_topk<T>(popular.p, uint32_t(n_ranked), cold_ids.p, st);
-        score_topk<T>(Pva.p, Qva.p, Kc, bt.p, t_row0, t_row1, uint32_t(n_ranked), t_cold.p, topk_ids.p, st);
+        if (!cold_ready) {   // the popularity ranking never changes after set_labels
+            vector_topk<T>(popular.p, uint32_t(n_ranked), cold_ids.p, st);
+            cold_ready = true;
+        }
+        const uint32_t nsplit = score_topk_splits(t_row1 - t_row0, uint32_t(n_ranked));
+        part_score.ensure(size_t(mt) * nsplit * 80);
+        part_id.ensure(size_t(mt) * nsplit * 80);
+        score_topk<T>(Pva.p, Qva.p, Kc, bt.p, t_row0, t_row1, uint32_t(n_ranked), t_cold.p, nsplit,
+                      part_score.p, part_id.p, topk_ids.p, st);
         acc64.zero(st);
         eval_metrics<T>(topk_ids.p, cold_ids.p, t_cold.p, t_rowptr.p, t_idx.p, t_row0, t_row1, Pva.p,
                         Qva.p, Kc, at.p, bt.p, popular.p, uint32_t(n), uint32_t(n_ranked), acc64.p, st);
@@ -965,15 +1045,7 @@ struct Problem final : CtxBase {
         const uint64_t want = which == 'P' ? rows_of(f1) : rows_of(f2);
         OC_REQUIRE(rows == want, "rows must equal the row count of the embedding's side");
         if (bk.side) download_unpadded(which == 'P' ? bk.P.p : bk.Q.p, kp, out, rows);
-        else {
-            // strided slice: copy the whole concatenated matrix rows then pick the columns
-            const T *base = (which == 'P' ? Pc.p : Qc.p);
-            std::vector<T> h(rows * Kc);
-            OC_CUDA(cudaMemcpyAsync(h.data(), base, rows * Kc * sizeof(T), cudaMemcpyDeviceToHost, st));
-            sync();
-            for (uint64_t i = 0; i < rows; ++i)
-                for (uint32_t d = 0; d < k; ++d) out[i * k + d] = double(h[i * Kc + size_t(bk.pair) * kp + d]);
-        }
+        else download_unpadded((which == 'P' ? Pc.p : Qc.p) + size_t(bk.pair) * kp, Kc, out, rows);
     }
     void get_csc(uint64_t *colptr, uint32_t *rowidx) override {
         OC_REQUIRE(YV.set, "labels not set");
@@ -994,12 +1066,17 @@ struct Problem final : CtxBase {
         out->hv_launches = hv_launches;
         out->hv_algo_bytes = hv_algo_bytes;
         out->hv_ms = hv_ms;
+        // side: grad / cg / update ; cross: grad / cg / update  (OCFFM_PROFILE >= 2)
+        out->ms_grad = ms[0]; out->ms_hess = ms[1]; out->ms_cgvec = ms[2];
+        out->ms_update = ms[3]; out->ms_gram = ms[4]; out->ms_eval = ms[5];
     }
     void reset_stats() override {
         sync();
         drain_hv_events();
         launches = cg_iters = nnz_trav = algo_bytes = hv_launches = hv_algo_bytes = 0;
         hv_ms = 0;
+        drain_phases();
+        for (double &v : ms) v = 0;
     }
     void synchronize() override { sync(); }
     void *stream() override { return st; }

@@ -110,8 +110,9 @@ void launch_gram(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb
 template <typename T, int KP, int TM, int TN>
 __global__ void __launch_bounds__(kThreads)
 k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restrict__ B,
-          T *__restrict__ C, uint64_t M) {
+          T *__restrict__ C, uint64_t M, Gate gate) {
     constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
+    if (!gate_open(gate)) return;
     constexpr int BK = sizeof(T) == 8 ? 16 : 32;   // keeps static shared memory under 48 KB
     __shared__ __align__(16) T As[BK][BM + 4];
     __shared__ __align__(16) T Bs[BK][KP];
@@ -167,11 +168,11 @@ k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restric
 }
 
 template <typename T, int KP, int TM, int TN>
-void launch_rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M,
+void launch_rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, Gate gate,
                     cudaStream_t s) {
     constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
     OC_LAUNCH((k_rowgemm<T, KP, TM, TN>), unsigned((M + BM - 1) / BM), kThreads, 0, s, A, lda, Ka, B,
-              C, M);
+              C, M, gate);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,6 +217,32 @@ __device__ __forceinline__ void finish_sum(double local, SolveScalars *sc, doubl
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
+k_pad_from_f64(const double *__restrict__ src, T *__restrict__ dst, uint64_t rows, uint32_t k,
+               uint32_t ld) {
+    const uint64_t n = rows * ld;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / ld;
+        const uint32_t c = uint32_t(i % ld);
+        dst[i] = c < k ? T(src[r * k + c]) : T(0);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_unpad_to_f64(const T *__restrict__ src, uint32_t ld, double *__restrict__ dst, uint64_t rows,
+               uint32_t k) {
+    const uint64_t n = rows * k;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / k;
+        const uint32_t c = uint32_t(i % k);
+        dst[i] = double(src[r * ld + c]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
 k_cg_init(T *__restrict__ G, const T *__restrict__ W, const T *__restrict__ freq, T lambda,
           T *__restrict__ R, T *__restrict__ V, T *__restrict__ S, uint64_t nvec, int kp4,
           SolveScalars *sc) {
@@ -240,6 +267,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_dir(T *__restrict__ V, const T *__restrict__ R, T *__restrict__ Hv, uint64_t nvec, int it,
          const SolveScalars *sc) {
+    if (!gate_open(Gate{sc, it})) return;
     const T beta = it > 0 ? T(sc->r2[it] / sc->r2[it - 1]) : T(0);
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -256,7 +284,8 @@ k_cg_dir(T *__restrict__ V, const T *__restrict__ R, T *__restrict__ Hv, uint64_
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_reg_dot(T *__restrict__ Hv, const T *__restrict__ V, const T *__restrict__ freq, T lambda,
-             uint64_t nvec, int kp4, int it, SolveScalars *sc) {
+             uint64_t nvec, int kp4, int it, SolveScalars *sc, int gated) {
+    if (gated && !gate_open(Gate{sc, it})) return;
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -274,6 +303,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T *__restrict__ Hv,
           uint64_t nvec, int it, SolveScalars *sc) {
+    if (!gate_open(Gate{sc, it})) return;
     const T alpha = T(sc->r2[it] / sc->vHv[it]);
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -389,16 +419,16 @@ void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb,
 }
 
 template <typename T>
-void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp,
+void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp, Gate gate,
              cudaStream_t s) {
     if (!M) return;
     switch (kp) {
-        case 4: launch_rowgemm<T, 4, 1, 4>(A, lda, Ka, B, C, M, s); break;
-        case 8: launch_rowgemm<T, 8, 1, 4>(A, lda, Ka, B, C, M, s); break;
-        case 16: launch_rowgemm<T, 16, 2, 4>(A, lda, Ka, B, C, M, s); break;
-        case 32: launch_rowgemm<T, 32, 4, 4>(A, lda, Ka, B, C, M, s); break;
-        case 64: launch_rowgemm<T, 64, 4, 8>(A, lda, Ka, B, C, M, s); break;
-        case 128: launch_rowgemm<T, 128, 4, 8>(A, lda, Ka, B, C, M, s); break;
+        case 4: launch_rowgemm<T, 4, 1, 4>(A, lda, Ka, B, C, M, gate, s); break;
+        case 8: launch_rowgemm<T, 8, 1, 4>(A, lda, Ka, B, C, M, gate, s); break;
+        case 16: launch_rowgemm<T, 16, 2, 4>(A, lda, Ka, B, C, M, gate, s); break;
+        case 32: launch_rowgemm<T, 32, 4, 4>(A, lda, Ka, B, C, M, gate, s); break;
+        case 64: launch_rowgemm<T, 64, 4, 8>(A, lda, Ka, B, C, M, gate, s); break;
+        case 128: launch_rowgemm<T, 128, 4, 8>(A, lda, Ka, B, C, M, gate, s); break;
         default: throw Error(-6, "padded latent dimension must be 4..128");
     }
 }
@@ -407,6 +437,18 @@ template <typename T>
 void convert_from_f64(const double *src, T *dst, uint64_t n, cudaStream_t s) {
     if (!n) return;
     OC_LAUNCH((k_convert<T>), ew_blocks(n), kThreads, 0, s, src, dst, n);
+}
+
+template <typename T>
+void pad_from_f64(const double *src, T *dst, uint64_t rows, uint32_t k, uint32_t ld, cudaStream_t s) {
+    if (!rows) return;
+    OC_LAUNCH((k_pad_from_f64<T>), ew_blocks(rows * ld), kThreads, 0, s, src, dst, rows, k, ld);
+}
+
+template <typename T>
+void unpad_to_f64(const T *src, uint32_t ld, double *dst, uint64_t rows, uint32_t k, cudaStream_t s) {
+    if (!rows) return;
+    OC_LAUNCH((k_unpad_to_f64<T>), ew_blocks(rows * k), kThreads, 0, s, src, ld, dst, rows, k);
 }
 
 template <typename T>
@@ -426,11 +468,11 @@ void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, const SolveScalars *sc,
 
 template <typename T>
 void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, int it,
-                SolveScalars *sc, cudaStream_t s) {
+                SolveScalars *sc, int gated, cudaStream_t s) {
     const uint64_t nvec = D * kp / 4;
     if (!nvec) return;
     OC_LAUNCH((k_cg_reg_dot<T>), ew_blocks(nvec), kThreads, 0, s, Hv, V, freq, lambda, nvec, kp / 4,
-              it, sc);
+              it, sc, gated);
 }
 
 template <typename T>
@@ -481,14 +523,16 @@ void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStr
     template void gram_stack<T>(const T *, uint32_t, uint32_t, const T *, uint32_t, int, uint32_t,  \
                                 uint32_t, const T *, double *, double *, double *, int,            \
                                 cudaStream_t);                                                      \
-    template void rowgemm<T>(const T *, uint32_t, uint32_t, const T *, T *, uint64_t, int,          \
+    template void rowgemm<T>(const T *, uint32_t, uint32_t, const T *, T *, uint64_t, int, Gate,    \
                              cudaStream_t);                                                         \
     template void convert_from_f64<T>(const double *, T *, uint64_t, cudaStream_t);                 \
+    template void pad_from_f64<T>(const double *, T *, uint64_t, uint32_t, uint32_t, cudaStream_t); \
+    template void unpad_to_f64<T>(const T *, uint32_t, double *, uint64_t, uint32_t, cudaStream_t); \
     template void cg_init<T>(T *, const T *, const T *, T, T *, T *, T *, uint64_t, int,            \
                              SolveScalars *, cudaStream_t);                                         \
     template void cg_dir<T>(T *, const T *, T *, uint64_t, int, const SolveScalars *, cudaStream_t); \
     template void cg_reg_dot<T>(T *, const T *, const T *, T, uint64_t, int, int, SolveScalars *,   \
-                                cudaStream_t);                                                      \
+                                int, cudaStream_t);                                                 \
     template void cg_step<T>(T *, T *, const T *, const T *, uint64_t, int, SolveScalars *,         \
                              cudaStream_t);                                                         \
     template void axpy<T>(T *, const T *, T, uint64_t, cudaStream_t);                               \

@@ -41,6 +41,20 @@ struct SolveScalars {       // device-resident fp64 scalars of one CG solve (ffm
     unsigned counter[4];
 };
 
+// Device-side gate of the speculatively enqueued CG iteration `it` (ffm.cpp:780: the loop runs
+// while g2 * cg_eps < r2): every kernel of an iteration returns at once when the stop test
+// already failed, so the host can enqueue iteration it+1 before it has read r2[it+1] back.
+struct Gate {
+    const SolveScalars *sc;
+    int it;   // < 0: always open
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ bool gate_open(const Gate &g) {
+    return g.it < 0 || g.sc->r2[0] * 9e-2 < g.sc->r2[g.it];
+}
+#endif
+constexpr Gate kNoGate{nullptr, -1};
+
 // ---- rows.cu ---------------------------------------------------------------------------------
 // C[i, 0:kp] = X_i * A   (UTX, ffm.cpp:314-331); C has leading dimension ldc
 template <typename T>
@@ -61,7 +75,7 @@ void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, ui
 // hs_cross row pass (ffm.cpp:715-738): phi = X_i V, tau = X_i (V QTQ), ka = sum_j (phi.q_j) q_j
 template <typename T>
 void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
-                     const T *V, const T *VQ, T w, T *Hv, int kp, cudaStream_t s);
+                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, cudaStream_t s);
 
 // ysum[row] = sum of y-tilde over the row (first half of gd_side's z_i, ffm.cpp:577-580)
 template <typename T>
@@ -71,7 +85,7 @@ void ytilde_rowsum(const OmegaView<T> &Y, T *ysum, int kp, cudaStream_t s);
 template <typename T>
 void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, const T *a1,
                const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
-               int kp, cudaStream_t s);
+               int kp, Gate gate, cudaStream_t s);
 
 // y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
 template <typename T>
@@ -101,11 +115,16 @@ void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb,
 
 // C[M x kp] = A[M x Ka] B[Ka x kp]   (T = P~ Gstack, ffm.cpp:663-670; VQTQ = V QTQ, ffm.cpp:799)
 template <typename T>
-void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp,
+void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp, Gate gate,
              cudaStream_t s);
 
 template <typename T>
 void convert_from_f64(const double *src, T *dst, uint64_t n, cudaStream_t s);
+// model blocks cross the C ABI as fp64 [rows x k]; the device keeps T [rows x ld] (zero padded)
+template <typename T>
+void pad_from_f64(const double *src, T *dst, uint64_t rows, uint32_t k, uint32_t ld, cudaStream_t s);
+template <typename T>
+void unpad_to_f64(const T *src, uint32_t ld, double *dst, uint64_t rows, uint32_t k, cudaStream_t s);
 
 // G += lambda * (freq ? freq[row] : 1) * W ; R = -G ; V = R ; S = 0 ; sc->r2[0] += ||G||^2
 template <typename T>
@@ -117,7 +136,7 @@ void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, const SolveScalars *sc,
 // Hv += lambda * (freq ? freq[row] : 1) * V ; sc->vHv[it] += V . Hv
 template <typename T>
 void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, int it,
-                SolveScalars *sc, cudaStream_t s);
+                SolveScalars *sc, int gated, cudaStream_t s);
 // alpha = r2[it]/vHv[it] ; S += alpha V ; R -= alpha Hv ; sc->r2[it+1] += ||R||^2
 template <typename T>
 void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc,
@@ -143,9 +162,12 @@ void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStr
 // ffm.cpp:1029-1046, 1074-1108): for test rows [row0,row1) scores z = bt + P~va_i . Q~va_j over
 // items [0, n_ranked) are produced tile by tile in shared memory and never written to HBM;
 // ids[row*80 + rank] gets the 80 best (first index wins ties), UINT32_MAX padded.
+// number of item-range splits score_topk wants for `rows` test rows (<= 32)
+uint32_t score_topk_splits(uint32_t rows, uint32_t n_ranked);
 template <typename T>
 void score_topk(const T *Pva, const T *Qva, uint32_t Kc, const T *bt, uint32_t row0, uint32_t row1,
-                uint32_t n_ranked, const uint8_t *cold, uint32_t *ids, cudaStream_t s);
+                uint32_t n_ranked, const uint8_t *cold, uint32_t nsplit, T *part_score,
+                uint32_t *part_id, uint32_t *ids, cudaStream_t s);
 // top-80 of a plain score vector (the `popular` ranking shared by all cold rows)
 template <typename T>
 void vector_topk(const T *z, uint32_t n_ranked, uint32_t *ids80, cudaStream_t s);

@@ -97,18 +97,28 @@ k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
     const uint32_t cnt = c & 0x7fffffffu;
     const bool first = (c >> 31) != 0;
     const T omw = T(1) - w, cst = w * (T(1) - r);
+    constexpr int U = G < 8 ? G : 8;
     V4<T> pk = zero4<T>();
+    const T *qbase = Q1 + lg * 4;
     for (uint32_t base = 0; base < cnt; base += G) {
         const bool ok = base + lg < cnt;
         const uint32_t t = beg + base + lg;
         const uint32_t j = ok ? Y.idx[t] : 0u;
         const T sc = ok ? omw * Y.yt[t] - cst : T(0);
-        const int nstep = min(int(G), int(cnt - base));
-#pragma unroll 4
-        for (int l = 0; l < nstep; ++l) {
-            const uint32_t jj = __shfl_sync(mask, j, l, G);
-            const T s = __shfl_sync(mask, sc, l, G);
-            fma4(pk, s, ldg4(Q1 + size_t(jj) * ldq + lg * 4));
+        const uint32_t rem = cnt - base;
+        if (rem >= uint32_t(G)) {
+#pragma unroll
+            for (int l0 = 0; l0 < G; l0 += U) {
+                V4<T> q[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+#pragma unroll
+                for (int u = 0; u < U; ++u) fma4(pk, __shfl_sync(mask, sc, l0 + u, G), q[u]);
+            }
+        } else {
+            for (uint32_t l = 0; l < rem; ++l)
+                fma4(pk, __shfl_sync(mask, sc, l, G), ldg4(qbase + size_t(__shfl_sync(mask, j, l, G)) * ldq));
         }
     }
     if (first) {
@@ -128,8 +138,10 @@ k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads)
 k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
-             const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv) {
+             const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate) {
     constexpr uint32_t kp = 4 * G;
+    constexpr int U = G < 8 ? G : 8;   // gathers kept in flight per lane
+    if (!gate_open(gate)) return;
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (item >= Y.n_items) return;
     const uint32_t lg = threadIdx.x % G;
@@ -138,6 +150,7 @@ k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
     const uint32_t cnt = c & 0x7fffffffu;
     const bool first = (c >> 31) != 0;
     const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
+    uint32_t j = lg < cnt ? Y.idx[beg + lg] : 0u;
     V4<T> phi = zero4<T>(), tau = zero4<T>();
     for (uint32_t t = xb; t < xe; ++t) {
         const size_t off = size_t(X.idx[t]) * kp + lg * 4;
@@ -146,17 +159,28 @@ k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
         if (first) fma4(tau, v, ldg4(VQ + off));
     }
     V4<T> ka = zero4<T>();
+    const T *qbase = Q1 + lg * 4;
     for (uint32_t base = 0; base < cnt; base += G) {
-        const bool ok = base + lg < cnt;
-        const uint32_t j = ok ? Y.idx[beg + base + lg] : 0u;
-        const int nstep = min(int(G), int(cnt - base));
-#pragma unroll 4
-        for (int l = 0; l < nstep; ++l) {
-            const uint32_t jj = __shfl_sync(mask, j, l, G);
-            const V4<T> q = ldg4(Q1 + size_t(jj) * ldq + lg * 4);
-            const T s = gsum<G>(dot4(phi, q), mask);
-            fma4(ka, s, q);
+        const uint32_t nb = base + G + lg;
+        const uint32_t jn = nb < cnt ? Y.idx[beg + nb] : 0u;   // next batch of column ids
+        const uint32_t rem = cnt - base;
+        if (rem >= uint32_t(G)) {
+#pragma unroll
+            for (int l0 = 0; l0 < G; l0 += U) {
+                V4<T> q[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+#pragma unroll
+                for (int u = 0; u < U; ++u) fma4(ka, gsum<G>(dot4(phi, q[u]), mask), q[u]);
+            }
+        } else {
+            for (uint32_t l = 0; l < rem; ++l) {
+                const V4<T> q = ldg4(qbase + size_t(__shfl_sync(mask, j, l, G)) * ldq);
+                fma4(ka, gsum<G>(dot4(phi, q), mask), q);
+            }
         }
+        j = jn;
     }
     const T omw = T(1) - w;
     V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
@@ -176,18 +200,33 @@ k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *_
     const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item];
     const uint32_t cnt = Y.wi_cnt[item] & 0x7fffffffu;
     if (cnt == 0) return;
+    constexpr int U = G < 8 ? G : 8;
     const V4<T> u = ldg4(Uown + size_t(row) * ldu + lg * 4);
+    const T *vbase = Vo + lg * 4;
     for (uint32_t base = 0; base < cnt; base += G) {
         const bool ok = base + lg < cnt;
         const uint32_t t = beg + base + lg;
         const uint32_t j = ok ? Y.idx[t] : 0u;
-        const int nstep = min(int(G), int(cnt - base));
+        const uint32_t rem = cnt - base;
         T mine = T(0);
-#pragma unroll 4
-        for (int l = 0; l < nstep; ++l) {
-            const uint32_t jj = __shfl_sync(mask, j, l, G);
-            const T s = gsum<G>(dot4(u, ldg4(Vo + size_t(jj) * ldv + lg * 4)), mask);
-            if (int(lg) == l) mine = s;
+        if (rem >= uint32_t(G)) {
+#pragma unroll
+            for (int l0 = 0; l0 < G; l0 += U) {
+                V4<T> q[U];
+#pragma unroll
+                for (int x = 0; x < U; ++x)
+                    q[x] = ldg4(vbase + size_t(__shfl_sync(mask, j, l0 + x, G)) * ldv);
+#pragma unroll
+                for (int x = 0; x < U; ++x) {
+                    const T s = gsum<G>(dot4(u, q[x]), mask);
+                    if (int(lg) == l0 + x) mine = s;
+                }
+            }
+        } else {
+            for (uint32_t l = 0; l < rem; ++l) {
+                const T s = gsum<G>(dot4(u, ldg4(vbase + size_t(__shfl_sync(mask, j, l, G)) * ldv)), mask);
+                if (lg == l) mine = s;
+            }
         }
         if (ok) Y.yt[t] += mine;
     }
@@ -212,8 +251,9 @@ template <typename T, int G, int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_side_rows(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, const T *__restrict__ a1,
             const T *__restrict__ sa1, const T *__restrict__ ysum, const double *__restrict__ bsum,
-            const T *__restrict__ V, T w, T r, T n1, T *__restrict__ Out) {
+            const T *__restrict__ V, T w, T r, T n1, T *__restrict__ Out, Gate gate) {
     constexpr uint32_t kp = 4 * G;
+    if (!gate_open(gate)) return;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (g >= uint64_t(X.row1 - X.row0)) return;
     const uint32_t lg = threadIdx.x % G;
@@ -331,10 +371,10 @@ void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, ui
 
 template <typename T>
 void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
-                     const T *V, const T *VQ, T w, T *Hv, int kp, cudaStream_t s) {
+                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, cudaStream_t s) {
     if (!Y.n_items) return;
     OC_DISPATCH_G(kp, OC_LAUNCH((k_hess_cross<T, G>), blocks_for(Y.n_items, G), kThreads, 0, s, Y, X,
-                                Q1, ldq, V, VQ, w, Hv));
+                                Q1, ldq, V, VQ, w, Hv, gate));
 }
 
 template <typename T>
@@ -347,15 +387,15 @@ void ytilde_rowsum(const OmegaView<T> &Y, T *ysum, int kp, cudaStream_t s) {
 template <typename T>
 void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, const T *a1,
                const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
-               int kp, cudaStream_t s) {
+               int kp, Gate gate, cudaStream_t s) {
     const uint64_t rows = X.row1 - X.row0;
     if (!rows) return;
     if (mode == 0) {
         OC_DISPATCH_G(kp, OC_LAUNCH((k_side_rows<T, G, 0>), blocks_for(rows, G), kThreads, 0, s, Y, X,
-                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out));
+                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out, gate));
     } else {
         OC_DISPATCH_G(kp, OC_LAUNCH((k_side_rows<T, G, 1>), blocks_for(rows, G), kThreads, 0, s, Y, X,
-                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out));
+                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out, gate));
     }
 }
 
@@ -402,11 +442,11 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
                                      const T *, const T *, const T *, const T *, T, T, T *, int,   \
                                      cudaStream_t);                                                \
     template void hess_cross_rows<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, \
-                                     const T *, const T *, T, T *, int, cudaStream_t);             \
+                                     const T *, const T *, T, T *, int, Gate, cudaStream_t);       \
     template void ytilde_rowsum<T>(const OmegaView<T> &, T *, int, cudaStream_t);                  \
     template void side_rows<T>(int, const OmegaView<T> &, const CsrView<T> &, const T *, const T *, \
                                const T *, const T *, const double *, const T *, T, T, T, T *, int, \
-                               cudaStream_t);                                                      \
+                               Gate, cudaStream_t);                                                \
     template void sddmm_add<T>(const OmegaView<T> &, const T *, uint32_t, const T *, uint32_t, int, \
                                cudaStream_t);                                                      \
     template void ytilde_base<T>(const OmegaView<T> &, const T *, const T *, cudaStream_t);        \

@@ -1,0 +1,519 @@
+// host/ffm_host.cpp -- data layer, model I/O and the ImpProblem front-end of the B200 build.
+//
+// The data layer reproduces the reference reader's CONTRACT (ffm.cpp:80-312: text format, what
+// m / n / f / Ds / nnx / popular / freq mean, which features are dropped, CSC order of transY)
+// with a single-pass buffer parser; the solver front-end only schedules C-ABI calls.
+#include "ffm.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <random>
+#include <stdexcept>
+
+using namespace std;
+
+namespace {
+
+struct Cursor {
+    const char *p, *end;
+    void skip_blank() { while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p; }
+    bool at_eol() const { return p >= end || *p == '\n'; }
+};
+
+// unsigned integer in the sense of `istream >> unsigned long`
+bool parse_ulong(Cursor &c, ImpLong &out) {
+    c.skip_blank();
+    if (c.at_eol() || *c.p < '0' || *c.p > '9') return false;
+    ImpLong v = 0;
+    while (c.p < c.end && *c.p >= '0' && *c.p <= '9') v = v * 10 + ImpLong(*c.p++ - '0');
+    out = v;
+    return true;
+}
+
+bool parse_sep(Cursor &c) {   // `istream >> char`: any non-blank character
+    c.skip_blank();
+    if (c.at_eol()) return false;
+    ++c.p;
+    return true;
+}
+
+bool parse_double(Cursor &c, double &out) {
+    c.skip_blank();
+    if (c.at_eol()) return false;
+    char buf[64];
+    size_t len = 0;
+    const char *q = c.p;
+    while (q < c.end && len + 1 < sizeof(buf) && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') buf[len++] = *q++;
+    buf[len] = 0;
+    char *stop = nullptr;
+    const double v = strtod(buf, &stop);
+    if (stop == buf) return false;
+    c.p += (stop - buf);
+    out = v;
+    return true;
+}
+
+// label list "j1,j2,...": every piece goes through stoi like the reference (ffm.cpp:95-96)
+void parse_labels(const char *b, const char *e, vector<ImpInt> &out) {
+    const char *p = b;
+    while (p < e) {
+        const char *q = p;
+        while (q < e && *q != ',') ++q;
+        out.push_back(ImpInt(stoi(string(p, q))));   // throws invalid_argument("stoi") on junk
+        p = q + 1;
+    }
+}
+
+string slurp(const string &path) {
+    string buf;
+    FILE *fh = fopen(path.c_str(), "rb");
+    if (!fh) return buf;   // like the reference: a missing file silently reads as empty (ffm.cpp:81-88)
+    fseek(fh, 0, SEEK_END);
+    const long sz = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    buf.resize(sz > 0 ? size_t(sz) : 0);
+    if (sz > 0 && fread(&buf[0], 1, size_t(sz), fh) != size_t(sz)) buf.clear();
+    fclose(fh);
+    return buf;
+}
+
+// The reference seeds its uniform init with a fast inverse square root (one Newton step on the
+// 64-bit magic-constant guess), so 0.1/sqrt(k) is only approximate; parity needs the same value.
+double approx_rsqrt(double x) {
+    const double half = 0.5 * x;
+    uint64_t bits;
+    memcpy(&bits, &x, sizeof bits);
+    bits = 0x5fe6eb50c7b537a9ULL - (bits >> 1);
+    memcpy(&x, &bits, sizeof bits);
+    return x * (1.5 - half * x * x);
+}
+
+void check(int rc, const char *what) {
+    if (rc != OCFFM_OK) throw runtime_error(string(what) + ": " + ocffm_last_error());
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// ImpData
+// ---------------------------------------------------------------------------------------------
+void ImpData::read(bool has_label, const ImpLong *ds) {
+    const string buf = slurp(file_name);
+    Cursor c{buf.data(), buf.data() + buf.size()};
+    vector<ImpInt> labels;
+    m = 0;
+    M.clear(); N.clear(); nnx.clear(); nny.clear();
+    y_rowptr.assign(1, 0);
+    y_idx.clear();
+    vector<ImpLong> xptr(1, 0);
+    while (c.p < c.end) {
+        const char *eol = static_cast<const char *>(memchr(c.p, '\n', size_t(c.end - c.p)));
+        const char *line_end = eol ? eol : c.end;
+        Cursor ln{c.p, line_end};
+        if (has_label) {
+            ln.skip_blank();
+            const char *b = ln.p;
+            while (ln.p < ln.end && *ln.p != ' ' && *ln.p != '\t' && *ln.p != '\r') ++ln.p;
+            labels.clear();
+            parse_labels(b, ln.p, labels);
+            for (ImpInt j : labels) {
+                n = max<ImpLong>(n, ImpLong(j) + 1);
+                y_idx.push_back(j);
+            }
+        }
+        ImpLong fid, idx;
+        double val;
+        for (;;) {
+            if (!parse_ulong(ln, fid) || !parse_sep(ln) || !parse_ulong(ln, idx) || !parse_sep(ln) ||
+                !parse_double(ln, val))
+                break;
+            f = max(f, fid + 1);
+            if (ds != nullptr && ds[fid] <= idx) continue;   // out-of-vocabulary test feature
+            Node nd;
+            nd.fid = ImpInt(fid);
+            nd.idx = idx;
+            nd.val = val;
+            N.push_back(nd);
+        }
+        xptr.push_back(N.size());
+        y_rowptr.push_back(y_idx.size());
+        ++m;
+        c.p = eol ? eol + 1 : c.end;
+    }
+    nnz_x = N.size();
+    nnx.resize(m);
+    nny.resize(m);
+    for (ImpLong i = 0; i < m; i++) {
+        nnx[i] = xptr[i + 1] - xptr[i];
+        nny[i] = y_rowptr[i + 1] - y_rowptr[i];
+    }
+    X.resize(m + 1);
+    Y.resize(m + 1);
+    for (ImpLong i = 0; i <= m; i++) X[i] = N.data() + xptr[i];
+    if (has_label) {
+        nnz_y = y_idx.size();
+        M.resize(nnz_y);
+        popular.assign(n, 0);
+        for (ImpLong t = 0; t < nnz_y; t++) {
+            M[t].idx = y_idx[t];
+            popular[y_idx[t]] += 1;
+        }
+        for (ImpLong i = 0; i <= m; i++) Y[i] = M.data() + y_rowptr[i];
+        ImpDouble total = 0;
+        for (ImpDouble v : popular) total += v;
+        for (ImpDouble &v : popular) v /= total;
+    }
+}
+
+void ImpData::split_fields() {
+    Xf.assign(f, FieldCSR());
+    Ds.assign(f, 0);
+    freq.assign(f, vector<ImpLong>());
+    for (ImpLong fi = 0; fi < f; fi++) Xf[fi].rowptr.assign(m + 1, 0);
+    for (ImpLong i = 0; i < m; i++)
+        for (const Node *x = X[i]; x < X[i + 1]; x++) Xf[x->fid].rowptr[i + 1]++;
+    for (ImpLong fi = 0; fi < f; fi++) {
+        FieldCSR &F = Xf[fi];
+        for (ImpLong i = 0; i < m; i++) F.rowptr[i + 1] += F.rowptr[i];
+        F.idx.resize(F.rowptr[m]);
+        F.val.resize(F.rowptr[m]);
+    }
+    vector<ImpLong> fill(f, 0);
+    for (ImpLong i = 0; i < m; i++)
+        for (const Node *x = X[i]; x < X[i + 1]; x++) {   // in-line order is kept inside a field
+            FieldCSR &F = Xf[x->fid];
+            const ImpLong t = fill[x->fid]++;
+            F.idx[t] = ImpInt(x->idx);
+            F.val[t] = x->val;
+            Ds[x->fid] = max(Ds[x->fid], x->idx + 1);
+        }
+    for (ImpLong fi = 0; fi < f; fi++) {
+        freq[fi].assign(Ds[fi], 0);
+        for (ImpInt id : Xf[fi].idx) freq[fi][id]++;
+    }
+    X.clear(); X.shrink_to_fit();
+    N.clear(); N.shrink_to_fit();
+}
+
+void ImpData::transY(const vector<Node *> &YT) {
+    // CSC of the label matrix ordered by (item, user): a stable counting sort over users in
+    // ascending order gives the order the reference obtains with std::sort (ffm.cpp:274-279)
+    n = YT.size() - 1;
+    vector<ImpLong> colptr(m + 1, 0);
+    ImpLong kept = 0;
+    for (ImpLong i = 0; i < n; i++)
+        for (const Node *y = YT[i]; y < YT[i + 1]; y++) {
+            if (y->idx >= m) continue;   // label beyond the item file
+            colptr[y->idx + 1]++;
+            kept++;
+        }
+    for (ImpLong j = 0; j < m; j++) colptr[j + 1] += colptr[j];
+    M.assign(kept, Node());
+    y_idx.assign(kept, 0);
+    vector<ImpLong> cur(colptr.begin(), colptr.end() - 1);
+    for (ImpLong i = 0; i < n; i++)
+        for (const Node *y = YT[i]; y < YT[i + 1]; y++) {
+            if (y->idx >= m) continue;
+            const ImpLong t = cur[y->idx]++;
+            M[t].idx = i;
+            M[t].val = y->val;
+            y_idx[t] = ImpInt(i);
+        }
+    nnz_y = kept;
+    y_rowptr = colptr;
+    Y.resize(m + 1);
+    for (ImpLong j = 0; j <= m; j++) Y[j] = M.data() + colptr[j];
+}
+
+void ImpData::print_data_info() {
+    cout << "File:" << file_name;
+    cout << setw(12) << "m:" << m;
+    cout << setw(12) << "n:" << n;
+    cout << setw(12) << "f:" << f;
+    cout << setw(12) << "d:" << Ds[0] << endl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ImpProblem
+// ---------------------------------------------------------------------------------------------
+ImpProblem::~ImpProblem() {
+    if (ctx) ocffm_destroy(ctx);
+}
+
+bool ImpProblem::block_exists(ImpInt f1, ImpInt f2) const {
+    return param->self_side || (f1 < fu && f2 >= fu);
+}
+
+ImpLong ImpProblem::block_rows(ImpInt fg) const { return fg < fu ? U->Ds[fg] : V->Ds[fg - fu]; }
+
+void ImpProblem::init_model_random() {
+    // Same calls, same order as the reference (ffm.cpp:71-78, 495-506): every matrix gets a
+    // minstd engine seeded with the next rand() and D*k draws from U(-s, s), s = 0.1*rsqrt~(k).
+    const ImpInt nr_blocks = f * (f + 1) / 2;
+    W.assign(nr_blocks, Vec());
+    H.assign(nr_blocks, Vec());
+    auto fill_uniform = [&](Vec &v, ImpLong rows) {
+        default_random_engine engine(rand());
+        const double s = 0.1 * approx_rsqrt(double(k));
+        uniform_real_distribution<ImpDouble> dist(-s, s);
+        v.resize(rows * k);
+        for (ImpDouble &x : v) x = dist(engine);
+    };
+    for (ImpInt f1 = 0; f1 < f; f1++)
+        for (ImpInt f2 = f1; f2 < f; f2++) {
+            if (!block_exists(f1, f2)) continue;
+            fill_uniform(W[index_of(f1, f2)], block_rows(f1));
+            fill_uniform(H[index_of(f1, f2)], block_rows(f2));
+        }
+}
+
+void ImpProblem::attach() {
+    ocffm_params prm;
+    prm.lambda = param->lambda;
+    prm.omega = param->omega;
+    prm.r = param->r;
+    prm.k = param->k;
+    prm.self_side = param->self_side;
+    prm.freq = param->freq;
+    prm.dtype = param->dtype;
+    prm.device = param->device;
+    check(ocffm_create(&ctx, &prm, fu, fv, m, n), "ocffm_create");
+    for (ImpInt fi = 0; fi < fu; fi++) {
+        const FieldCSR &F = U->Xf[fi];
+        check(ocffm_set_field(ctx, OCFFM_SIDE_U, fi, m, U->Ds[fi], F.rowptr.data(), F.idx.data(), F.val.data()),
+              "ocffm_set_field(U)");
+    }
+    for (ImpInt fi = 0; fi < fv; fi++) {
+        const FieldCSR &F = V->Xf[fi];
+        check(ocffm_set_field(ctx, OCFFM_SIDE_V, fi, n, V->Ds[fi], F.rowptr.data(), F.idx.data(), F.val.data()),
+              "ocffm_set_field(V)");
+    }
+    if (V->nnz_y != U->nnz_y)
+        throw invalid_argument("a label exceeds the number of lines of the item file");
+    check(ocffm_set_labels(ctx, m, U->y_rowptr.data(), U->y_idx.data(), V->y_rowptr.data(), V->y_idx.data(),
+                           U->n, U->popular.data()),
+          "ocffm_set_labels");
+    if (!Uva->file_name.empty()) {
+        mt = Uva->m;
+        const vector<ImpLong> empty_ptr(mt + 1, 0);
+        for (ImpInt fi = 0; fi < fu; fi++) {
+            if (fi < Uva->Xf.size()) {
+                const FieldCSR &F = Uva->Xf[fi];
+                check(ocffm_set_field(ctx, OCFFM_SIDE_T, fi, mt, U->Ds[fi], F.rowptr.data(), F.idx.data(),
+                                      F.val.data()),
+                      "ocffm_set_field(T)");
+            } else {   // the test file never mentions this field
+                check(ocffm_set_field(ctx, OCFFM_SIDE_T, fi, mt, U->Ds[fi], empty_ptr.data(), nullptr, nullptr),
+                      "ocffm_set_field(T)");
+            }
+        }
+        check(ocffm_set_test_labels(ctx, mt, Uva->y_rowptr.data(), Uva->y_idx.data(), Uva->nnx.data()),
+              "ocffm_set_test_labels");
+    }
+}
+
+void ImpProblem::push_model() {
+    for (ImpInt f1 = 0; f1 < f; f1++)
+        for (ImpInt f2 = f1; f2 < f; f2++) {
+            if (!block_exists(f1, f2)) continue;
+            const ImpInt b = index_of(f1, f2);
+            check(ocffm_set_block(ctx, f1, f2, 'W', W[b].data(), block_rows(f1)), "ocffm_set_block(W)");
+            check(ocffm_set_block(ctx, f1, f2, 'H', H[b].data(), block_rows(f2)), "ocffm_set_block(H)");
+        }
+    host_model_stale = false;
+}
+
+void ImpProblem::pull_model() const {
+    if (!host_model_stale || !ctx) return;
+    for (ImpInt f1 = 0; f1 < f; f1++)
+        for (ImpInt f2 = f1; f2 < f; f2++) {
+            if (!block_exists(f1, f2)) continue;
+            const ImpInt b = index_of(f1, f2);
+            check(ocffm_get_block(ctx, f1, f2, 'W', W[b].data(), block_rows(f1)), "ocffm_get_block(W)");
+            check(ocffm_get_block(ctx, f1, f2, 'H', H[b].data(), block_rows(f2)), "ocffm_get_block(H)");
+        }
+    host_model_stale = false;
+}
+
+void ImpProblem::prepare_shapes() {
+    lambda = param->lambda;
+    w = param->omega;
+    r = param->r;
+    m = U->m;
+    n = V->m;
+    fu = ImpInt(U->f);
+    fv = ImpInt(V->f);
+    f = fu + fv;
+    k = param->k;
+}
+
+void ImpProblem::init() {
+    prepare_shapes();
+    if (W.empty()) init_model_random();   // a model loaded by load_binary_model() is kept
+    attach();
+    push_model();
+    check(ocffm_init_state(ctx), "ocffm_init_state");
+}
+
+void ImpProblem::one_epoch() {
+    check(ocffm_one_epoch(ctx), "ocffm_one_epoch");
+    host_model_stale = true;
+}
+
+ImpDouble ImpProblem::func() {
+    double v = 0;
+    check(ocffm_objective(ctx, &v), "ocffm_objective");
+    return v;
+}
+
+void ImpProblem::init_va(ImpInt size) {
+    if (Uva->file_name.empty()) return;
+    mt = Uva->m;
+    va_loss_prec.assign(size, 0);
+    va_loss_ndcg.assign(size, 0);
+    top_k.resize(size);
+    // header line of the log, byte-compatible with the reference (ffm.cpp:899-912) so that
+    // script/logs.tools keep working
+    cout << "iter";
+    ImpInt cut = 5;
+    for (ImpInt i = 0; i < size; i++, cut *= 2) {
+        top_k[i] = cut;
+        cout << setw(9) << "( p@ " << cut << ", " << setw(6) << "nDCG@" << cut << " )";
+    }
+    cout << setw(12) << "ploss" << endl;
+}
+
+void ImpProblem::validate() {
+    double prec[5], ndcg[5], pl = 0;
+    check(ocffm_validate(ctx, prec, ndcg, &pl, nullptr), "ocffm_validate");
+    for (size_t i = 0; i < top_k.size() && i < 5; i++) {
+        va_loss_prec[i] = prec[i];
+        va_loss_ndcg[i] = ndcg[i];
+    }
+    loss = pl;
+}
+
+void ImpProblem::print_epoch_info(ImpInt t) {
+    cout << setw(2) << t + 1;
+    if (!Uva->file_name.empty()) {
+        for (size_t i = 0; i < top_k.size(); i++) {
+            cout << setw(9) << "( " << setprecision(3) << va_loss_prec[i] * 100 << " ,";
+            cout << setw(6) << setprecision(3) << va_loss_ndcg[i] * 100 << " )";
+        }
+        cout << setw(13) << setprecision(3) << loss;
+    }
+    cout << endl;
+}
+
+void ImpProblem::solve() {
+    init_va(5);
+    for (ImpInt iter = 0; iter < param->nr_pass; iter++) {
+        one_epoch();
+        if (!Uva->file_name.empty() && iter % 10 == 9) {   // ffm.cpp:1155-1158
+            validate();
+            print_epoch_info(iter);
+        }
+    }
+}
+
+// ---- model output: layouts of ffm.cpp:1163-1267 -------------------------------------------------
+void ImpProblem::write_header(ofstream &o_f) const {
+    o_f << f << endl << fu << endl << fv << endl << k << endl;
+    for (ImpInt fi = 0; fi < fu; fi++) o_f << U->Ds[fi] << endl;
+    for (ImpInt fi = 0; fi < fv; fi++) o_f << V->Ds[fi] << endl;
+}
+
+void ImpProblem::write_W_and_H(ofstream &o_f) const {
+    pull_model();
+    auto rows_out = [&](const Vec &blk, ImpLong rows, char tag, ImpInt fi, ImpInt fj) {
+        for (ImpLong row = 0; row < rows; row++) {
+            o_f << tag << ',' << fi << ',' << fj << ',' << row;
+            for (ImpInt d = 0; d < k; d++) o_f << " " << blk[row * k + d];
+            o_f << endl;
+        }
+    };
+    for (ImpInt fi = 0; fi < f; fi++)
+        for (ImpInt fj = fi; fj < f; fj++) {
+            if (!block_exists(fi, fj)) continue;
+            rows_out(W[index_of(fi, fj)], block_rows(fi), 'W', fi, fj);
+            rows_out(H[index_of(fi, fj)], block_rows(fj), 'H', fi, fj);
+        }
+}
+
+void save_model(const ImpProblem &prob, string &model_path) {
+    ofstream f_out(model_path, ios::out | ios::trunc);
+    prob.write_header(f_out);
+    prob.write_W_and_H(f_out);
+}
+
+void ImpProblem::save_binary_model(string &model_path) {
+    pull_model();
+    ofstream of(model_path, ios::binary | ios::trunc);
+    auto put = [&](const void *p, size_t bytes) { of.write(static_cast<const char *>(p), streamsize(bytes)); };
+    put(&f, sizeof(ImpInt));
+    put(&fu, sizeof(ImpInt));
+    put(&fv, sizeof(ImpInt));
+    put(&k, sizeof(ImpInt));
+    put(U->Ds.data(), sizeof(ImpLong) * fu);
+    put(V->Ds.data(), sizeof(ImpLong) * fv);
+    for (ImpInt fi = 0; fi < f; fi++)
+        for (ImpInt fj = fi; fj < f; fj++) {
+            if (!block_exists(fi, fj)) continue;
+            ImpInt fij = index_of(fi, fj);
+            ImpLong wn = W[fij].size(), hn = H[fij].size();
+            put(&fij, sizeof(ImpInt));
+            put(&wn, sizeof(ImpLong));
+            put(&hn, sizeof(ImpLong));
+            put(W[fij].data(), sizeof(ImpDouble) * wn);
+            put(H[fij].data(), sizeof(ImpDouble) * hn);
+        }
+}
+
+// A loader that loads.  Call after U/V are read and before init(): init() then
+// keeps these blocks instead of drawing random ones, which is also how parity tests inject state.
+void ImpProblem::load_binary_model(string &model_path) {
+    ifstream in(model_path, ios::binary);
+    if (!in) throw invalid_argument("cannot open model file " + model_path);
+    auto get = [&](void *p, size_t bytes) {
+        in.read(static_cast<char *>(p), streamsize(bytes));
+        if (!in) throw invalid_argument("truncated model file " + model_path);
+    };
+    ImpInt mf, mfu, mfv, mk;
+    get(&mf, sizeof mf); get(&mfu, sizeof mfu); get(&mfv, sizeof mfv); get(&mk, sizeof mk);
+    if (mfu != U->f || mfv != V->f || mk != param->k)
+        throw invalid_argument("model file does not match the data (fields or k differ)");
+    fu = mfu; fv = mfv; f = mf; k = mk;
+    vector<ImpLong> du(fu), dv(fv);
+    get(du.data(), sizeof(ImpLong) * fu);
+    get(dv.data(), sizeof(ImpLong) * fv);
+    for (ImpInt i = 0; i < fu; i++)
+        if (du[i] != U->Ds[i]) throw invalid_argument("model file does not match the data (Ds differ)");
+    for (ImpInt i = 0; i < fv; i++)
+        if (dv[i] != V->Ds[i]) throw invalid_argument("model file does not match the data (Ds differ)");
+    const ImpInt nr_blocks = f * (f + 1) / 2;
+    W.assign(nr_blocks, Vec());
+    H.assign(nr_blocks, Vec());
+    for (ImpInt fi = 0; fi < f; fi++)
+        for (ImpInt fj = fi; fj < f; fj++) {
+            if (!block_exists(fi, fj)) continue;
+            ImpInt fij;
+            ImpLong wn, hn;
+            get(&fij, sizeof fij); get(&wn, sizeof wn); get(&hn, sizeof hn);
+            if (fij != index_of(fi, fj) || wn != block_rows(fi) * k || hn != block_rows(fj) * k)
+                throw invalid_argument("model file block layout mismatch");
+            W[fij].resize(wn);
+            H[fij].resize(hn);
+            get(W[fij].data(), sizeof(ImpDouble) * wn);
+            get(H[fij].data(), sizeof(ImpDouble) * hn);
+        }
+    if (ctx) {
+        push_model();
+        check(ocffm_init_state(ctx), "ocffm_init_state");
+    }
+}

@@ -1,0 +1,133 @@
+// host/train.cpp -- the `train` command of the B200 build.  Same positional arguments
+// (item file first, then the training file), same flags and same error behaviour as the
+// reference driver (train.cpp:34-207); the work happens in libocffm_cuda.so.
+//
+//   train [options] item_feature_file train_file
+//
+// Flags of the reference: -l -k -t -w -r -c -p -o --ns --freq (parsing stops at the first token
+// that is not a flag, numeric flags only need one digit somewhere in their value, exactly like
+// is_numerical there).  Added: --f64 (fp64 on the device), --device N, --load <binary model>,
+// --save-binary <path>, --predict-only (evaluate a loaded model once, no training).
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+#include "ffm.h"
+
+using namespace std;
+
+namespace {
+
+struct Option {
+    shared_ptr<Parameter> param = make_shared<Parameter>();
+    string item_path, train_path, test_path, model_path, load_path, binary_path;
+    bool predict_only = false;
+};
+
+bool has_digit(const char *s) {
+    for (; *s; ++s)
+        if (isdigit(static_cast<unsigned char>(*s))) return true;
+    return false;
+}
+
+const char *kUsage =
+    "usage: train [options] item_feature_file train_file\n"
+    "\n"
+    "options:\n"
+    "-l <lambda_2>: set regularization coefficient on r regularizer (default 1e-5)\n"
+    "-t <iter>: set number of iterations (default 20)\n"
+    "-p <path>: set path to test set\n"
+    "-o <path>: set path to save model file\n"
+    "-w <omega>: set cost weight for the negatives\n"
+    "-r <rating>: set rating for the negatives\n"
+    "-c <threads>: set number of host threads (kept for compatibility; the solver runs on the GPU)\n"
+    "-k <rank>: set number of rank\n"
+    "--ns: drop the same-side blocks\n"
+    "--freq: enable freq-aware lambda\n"
+    "--f64: solve in fp64 on the device (default fp32 storage, fp64 scalars)\n"
+    "--device <n>: CUDA device ordinal\n"
+    "--load <path>: start from a binary model (save_binary_model layout)\n"
+    "--save-binary <path>: also write the binary model\n"
+    "--predict-only: evaluate the loaded model on the test set and exit\n";
+
+// value of a numeric flag; `miss` is thrown when the value is absent, `bad` when it has no digit
+const char *numeric_value(int argc, char **argv, int &i, const char *miss, const char *bad) {
+    if (i + 1 >= argc) throw invalid_argument(miss);
+    ++i;
+    if (!has_digit(argv[i])) throw invalid_argument(bad);
+    return argv[i];
+}
+
+Option parse_option(int argc, char **argv) {
+    if (argc == 1) throw invalid_argument(kUsage);
+    Option opt;
+    Parameter &p = *opt.param;
+    int i = 1;
+    for (; i < argc; i++) {
+        const string a = argv[i];
+        if (a == "-l") p.lambda = atof(numeric_value(argc, argv, i, "need to specify l regularization coefficient after -l", "-l should be followed by a number"));
+        else if (a == "-k") p.k = atoi(numeric_value(argc, argv, i, "need to specify rank after -k", "-k should be followed by a number"));
+        else if (a == "-t") p.nr_pass = atoi(numeric_value(argc, argv, i, "need to specify max number of iterations after -t", "-t should be followed by a number"));
+        else if (a == "-w") p.omega = atof(numeric_value(argc, argv, i, "need to specify the negative weight after -w", "-w should be followed by a number"));
+        else if (a == "-r") p.r = atof(numeric_value(argc, argv, i, "need to specify the negative rating after -r", "-r should be followed by a number"));
+        else if (a == "-c") p.nr_threads = ImpInt(atof(numeric_value(argc, argv, i, "missing core numbers after -c", "-c should be followed by a number")));
+        else if (a == "--device") p.device = atoi(numeric_value(argc, argv, i, "missing ordinal after --device", "--device should be followed by a number"));
+        else if (a == "-p" || a == "-o" || a == "--load" || a == "--save-binary") {
+            if (i == argc - 1) throw invalid_argument("need to specify path after " + a);
+            const string v = argv[++i];
+            (a == "-p" ? opt.test_path : a == "-o" ? opt.model_path : a == "--load" ? opt.load_path : opt.binary_path) = v;
+        } else if (a == "--ns") p.self_side = false;
+        else if (a == "--freq") p.freq = true;
+        else if (a == "--f64") p.dtype = OCFFM_F64;
+        else if (a == "--predict-only") opt.predict_only = true;
+        else break;   // first non-flag token ends option parsing
+    }
+    if (i >= argc) throw invalid_argument("training data not specified");
+    opt.item_path = argv[i++];
+    if (i < argc) opt.train_path = argv[i++];
+    return opt;
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    try {
+        Option opt = parse_option(argc, argv);
+        shared_ptr<ImpData> U = make_shared<ImpData>(opt.train_path);
+        shared_ptr<ImpData> V = make_shared<ImpData>(opt.item_path);
+        shared_ptr<ImpData> Ut = make_shared<ImpData>(opt.test_path);
+
+        U->read(true);
+        U->split_fields();
+        V->read(false);
+        V->transY(U->Y);
+        V->split_fields();
+        if (!Ut->file_name.empty()) {
+            Ut->read(true, U->Ds.data());
+            Ut->split_fields();
+        }
+
+        ImpProblem prob(U, Ut, V, opt.param);
+        if (!opt.load_path.empty()) prob.load_binary_model(opt.load_path);
+        prob.init();
+        if (opt.predict_only) {
+            if (Ut->file_name.empty()) throw invalid_argument("--predict-only needs -p <test set>");
+            prob.init_va(5);
+            prob.validate();
+            prob.print_epoch_info(0);
+        } else {
+            prob.solve();
+        }
+        if (!opt.model_path.empty()) save_model(prob, opt.model_path);
+        if (!opt.binary_path.empty()) prob.save_binary_model(opt.binary_path);
+    } catch (invalid_argument &e) {
+        cerr << e.what() << endl;
+        return 1;
+    } catch (runtime_error &e) {
+        cerr << "train: " << e.what() << endl;
+        return 2;
+    }
+    return 0;
+}

@@ -64,6 +64,22 @@ def run_case(case):
           "func", d.get("epochs.func"), "cg", d["epochs.cg_iters"])
 
 
+def run_cli(case):
+    """stdout and text model of the unmodified reference CLI (train.cpp) -- the drop-in contract."""
+    out_dir = os.path.join(GOLD, case["name"])
+    item_p, tr_p, te_p = (os.path.join(out_dir, f"{case['name']}.{e}") for e in ("item", "tr", "te"))
+    flags = [x for x in case["flags"]]
+    flags[flags.index("-t") + 1] = "20"          # two log lines (iterations 10 and 20)
+    model = os.path.join(out_dir, "ref_model.txt")
+    out = subprocess.check_output([os.path.join(HERE, "_ref", "train_ref")] + flags +
+                                  ["-c", "1", "-p", te_p, "-o", model, item_p, tr_p], text=True)
+    with open(os.path.join(out_dir, "ref_stdout.txt"), "w") as fh:
+        fh.write(out)
+    with open(os.path.join(out_dir, "cli_flags.txt"), "w") as fh:
+        fh.write(" ".join(flags) + "\n")
+    print(case["name"], "cli:\n" + out)
+
+
 def run_ndcg_fixture():
     tool = os.path.join(REF, "script", "nDCG_degub_tool")
     out = subprocess.check_output(
@@ -101,4 +117,6 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
     for c in CASES:
         run_case(c)
+    for c in CASES[:3]:
+        run_cli(c)
     run_ndcg_fixture()
