@@ -191,6 +191,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import dist_util
     import ocffm
     import synth
 
@@ -199,10 +200,8 @@ def main():
     torch.cuda.set_device(local_rank)
     comm = None
     if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-        box = [ocffm.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        comm = (world, rank, box[0])
+        dist_util.init("nccl")
+        comm = (world, rank, dist_util.share_unique_id(ocffm.comm_unique_id))
 
     t_gen = time.time()
     gen_kw = dict(shape=shape, seed=args.seed, scale=args.scale,
@@ -253,10 +252,7 @@ def main():
     sampler.stop_flag = True
     ms = ev0.elapsed_time(ev1)
     st = prob.stats()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = dist_util.max_over_ranks(ms)
     sec = ms / 1e3
     value = st.nnz_traversed / sec
     objective = prob.objective()
@@ -282,10 +278,7 @@ def main():
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ems], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
+        ems = dist_util.max_over_ranks(ems)
         fx = ds.users.f * ds.items.f
         flops = 2.0 * ds.test.rows * ds.train.n_items * fx * k
         eval_info = dict(users_per_s=ds.test.rows / (ems / 1e3), ms=ems, m_t=ds.test.rows,
@@ -308,10 +301,7 @@ def main():
             host_model[key] = prob.get_block(*key)         # D2H
     prob.synchronize()
     e2e_sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
+    e2e_sec = dist_util.max_over_ranks(e2e_sec)
     st2 = prob.stats()
     e2e = dict(value=st2.nnz_traversed / e2e_sec, unit="nnz/s", h2d_bytes_per_step=bytes_model,
                d2h_bytes_per_step=bytes_model, steps=e2e_steps, sec_per_step=e2e_sec / e2e_steps,

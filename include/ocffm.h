@@ -77,6 +77,9 @@ OCFFM_API int ocffm_destroy(ocffm_ctx *ctx);
  * any means (bench.py uses torch.distributed), every rank calls ocffm_comm_init BEFORE any
  * data is set.  With nranks == 1 (or never called) no NCCL symbol is touched. */
 OCFFM_API int ocffm_comm_unique_id(void *id128);
+/* the contiguous row slice [lo, hi) rank `rank` of `nranks` owns out of `rows` rows (pure host
+ * arithmetic, usable without a GPU; the same rule shards users, items and test rows) */
+OCFFM_API int ocffm_shard_range(uint64_t rows, int nranks, int rank, uint64_t *lo, uint64_t *hi);
 OCFFM_API int ocffm_comm_init(ocffm_ctx *ctx, int nranks, int rank, const void *id128);
 
 /* ---- data: ImpData after read()/split_fields()/transY() (ffm.h:59-79, ffm.cpp:80-294) ----

@@ -1210,6 +1210,15 @@ int ocffm_comm_unique_id(void *id128) {
         memcpy(id128, &uid, sizeof(uid));
     });
 }
+int ocffm_shard_range(uint64_t rows, int nranks, int rank, uint64_t *lo, uint64_t *hi) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi) {
+        ocffm::g_last_error = "bad rank / nranks";
+        return OCFFM_E_INVALID;
+    }
+    *lo = rows * uint64_t(rank) / uint64_t(nranks);
+    *hi = rows * uint64_t(rank + 1) / uint64_t(nranks);
+    return OCFFM_OK;
+}
 int ocffm_comm_init(ocffm_ctx *ctx, int nranks, int rank, const void *id128) {
     return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.comm_init(nranks, rank, id128); });
 }

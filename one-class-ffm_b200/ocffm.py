@@ -42,7 +42,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "ocffm_abi_version", "ocffm_last_error", "ocffm_device_count", "ocffm_create", "ocffm_destroy",
-    "ocffm_comm_unique_id", "ocffm_comm_init", "ocffm_set_field", "ocffm_set_labels",
+    "ocffm_comm_unique_id", "ocffm_shard_range", "ocffm_comm_init", "ocffm_set_field", "ocffm_set_labels",
     "ocffm_set_test_labels", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
     "ocffm_solve_block", "ocffm_one_epoch", "ocffm_grad", "ocffm_hess_vec", "ocffm_cg",
     "ocffm_objective", "ocffm_validate", "ocffm_get_vec", "ocffm_get_embed", "ocffm_get_csc",
@@ -70,6 +70,7 @@ def lib():
         L.ocffm_destroy.argtypes = [vp]
         L.ocffm_comm_unique_id.argtypes = [vp]
         L.ocffm_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.ocffm_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
         L.ocffm_set_field.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, u64p, u32p, f64p]
         L.ocffm_set_labels.argtypes = [vp, C.c_uint64, u64p, u32p, u64p, u32p, C.c_uint64, f64p]
         L.ocffm_set_test_labels.argtypes = [vp, C.c_uint64, u64p, u32p, u64p]
@@ -112,6 +113,14 @@ def _u32(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def shard_range(rows: int, nranks: int, rank: int) -> Tuple[int, int]:
+    lo, hi = C.c_uint64(0), C.c_uint64(0)
+    rc = lib().ocffm_shard_range(rows, nranks, rank, C.byref(lo), C.byref(hi))
+    if rc:
+        raise OcffmError(rc, lib().ocffm_last_error().decode())
+    return int(lo.value), int(hi.value)
 
 
 def comm_unique_id() -> bytes:

@@ -1,0 +1,43 @@
+"""Rows sharded over 2 GPUs (NCCL all-reduce of Grams / gradients / Hessian-vector products,
+all-gather of updated embeddings) must reproduce the single-GPU solve."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import ocffm
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+WORKER = os.path.join(ROOT, "tests", "multi_gpu_worker.py")
+
+
+def run(world, out, dtype):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", WORKER, out, dtype]
+    if world == 1:
+        cmd = [sys.executable, WORKER, out, dtype]
+    subprocess.run(cmd, check=True, timeout=600, capture_output=True)
+    return np.load(out)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_two_ranks_match_one(dtype):
+    if ocffm.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with tempfile.TemporaryDirectory() as tmp:
+        one = run(1, os.path.join(tmp, "one.npz"), dtype)
+        two = run(2, os.path.join(tmp, "two.npz"), dtype)
+    tol = 1e-9 if dtype == "f64" else 2e-3
+    if dtype == "f64":
+        assert list(one["cgs"]) == list(two["cgs"])
+    assert np.allclose(one["objs"], two["objs"], rtol=tol if dtype == "f64" else 2e-4)
+    for k in one.files:
+        if k[0] == "W" or k in ("a", "b"):
+            scale = np.max(np.abs(one[k])) + 1e-300
+            assert np.max(np.abs(one[k] - two[k])) <= tol * 50 * scale, k
+    assert np.allclose(one["ndcg"], two["ndcg"], rtol=1e-6 if dtype == "f64" else 2e-2)
+    assert np.allclose(one["ploss"], two["ploss"], rtol=1e-6 if dtype == "f64" else 1e-3)
