@@ -37,6 +37,7 @@ WORKLOADS = {
     "C3": ("C3", 16, 20_000),
     "C4": ("C4", 32, 20_000),
 }
+SHAPE_M = {"C1": 10_000, "C2": 30_000, "C3": 8_000_000, "C4": 4_000_000}
 CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02}
 
 
@@ -204,26 +205,33 @@ def main():
         comm = (world, rank, dist_util.share_unique_id(ocffm.comm_unique_id))
 
     t_gen = time.time()
-    gen_kw = dict(shape=shape, seed=args.seed, scale=args.scale,
-                  test_rows=0 if args.no_eval else max(64, int(test_rows * args.scale)))
+    n_test = 0 if args.no_eval else max(64, int(test_rows * args.scale))
     if world > 1:
-        # one rank generates, the others read its pickle (the generator is seeded, this only saves time)
+        # WEAK scaling: every GPU brings one block of the shape's users (m = 30k x N for C2) over
+        # the same items; each rank generates its own seeded block, blocks are exchanged through
+        # /tmp (one node), every rank assembles the full set (it needs both orientations of Omega)
         import pickle
-        cache = os.path.join(tempfile.gettempdir(), f"ocffm_{shape}_{args.seed}_{args.scale}_{gen_kw['test_rows']}.pkl")
-        if rank == 0:
-            ds = synth.generate(**gen_kw)
-            with open(cache + ".tmp", "wb") as fh:
-                pickle.dump(ds, fh, protocol=4)
-            os.replace(cache + ".tmp", cache)
+        tag = os.path.join(tempfile.gettempdir(), f"ocffm_{shape}_{args.seed}_w{world}")
+        blk = synth.user_block(shape, args.seed, rank, world)
+        with open(f"{tag}_b{rank}.tmp", "wb") as fh:
+            pickle.dump(blk, fh, protocol=4)
+        os.replace(f"{tag}_b{rank}.tmp", f"{tag}_b{rank}.pkl")
         dist.barrier()
-        if rank != 0:
-            with open(cache, "rb") as fh:
-                ds = pickle.load(fh)
+        blocks = []
+        for b in range(world):
+            with open(f"{tag}_b{b}.pkl", "rb") as fh:
+                blocks.append(pickle.load(fh))
+        ds = synth.assemble_blocks(shape, args.seed, blocks, test_rows=n_test)
+        dist.barrier()
+        if rank == 0:
+            for b in range(world):
+                os.remove(f"{tag}_b{b}.pkl")
     else:
-        ds = synth.generate(**gen_kw)
+        ds = synth.generate(shape=shape, seed=args.seed, scale=args.scale, test_rows=n_test)
     t_gen = time.time() - t_gen
     config.update(m=ds.m, n=ds.n, nnz_y=int(ds.train.idx.size), fu=ds.users.f, fv=ds.items.f,
-                  m_t=0 if ds.test is None else ds.test.rows, parallelism=f"rows sharded over {world} GPU(s)")
+                  m_t=0 if ds.test is None else ds.test.rows, parallelism=f"rows sharded over {world} GPU(s)" + (
+                      "" if world == 1 else f"; weak scaling: {world} blocks of {SHAPE_M.get(shape, 0)} users over the same items"))
     dtype = ocffm.F32 if args.dtype == "f32" else ocffm.F64
     os.environ.setdefault("OCFFM_PROFILE", "1")     # CUDA events around every hv_cross launch
     prob = ocffm.Problem(ds, k=k, dtype=dtype, device=local_rank, self_side=not args.ns, comm=comm, **HYPER)
@@ -324,7 +332,7 @@ def main():
     if rank == 0:
         line = dict(metric="nnz_per_s", value=value, unit="nnz/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
-                    scaling="strong", vs_baseline=None, dtype=args.dtype, data="synthetic", config=config,
+                    scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic", config=config,
                     sec_per_outer_iteration=sec / args.steps, cg_iters_per_step=st.cg_iters / args.steps,
                     objective=objective, gpu_launches=int(st.kernel_launches), e2e=e2e, roofline=roofline,
                     cpu_baseline=cpu, eval=eval_info, clocks=sampler.summary(), datagen_s=t_gen)

@@ -198,7 +198,7 @@ struct Problem final : CtxBase {
     std::vector<Field> XU, XV, XT;
     Omega YU, YV;
     DevBuf<uint32_t> t_rowptr, t_idx, topk_ids, cold_ids, part_id;
-    DevBuf<T> part_score;
+    DevBuf<T> part_score, ev_Pva, ev_Qva, ev_at, ev_bt, ev_t1, ev_t2;
     bool cold_ready = false;
     DevBuf<uint8_t> t_cold;
     std::vector<uint8_t> h_cold;
@@ -963,13 +963,15 @@ struct Problem final : CtxBase {
         OC_REQUIRE(test_set, "test labels not set");
         for (auto &bk : blocks)
             if (bk.exists) OC_REQUIRE(bk.has_w && bk.has_h, "a parameter block was never set");
-        DevBuf<T> Pva, Qva, at, bt, t1, t2;
-        Pva.alloc(mt * Kc);
-        Qva.alloc(n * Kc);
-        at.alloc(mt); bt.alloc(n);
-        at.zero(st); bt.zero(st);
-        t1.alloc(std::max(mt, n) * kp);
-        t2.alloc(std::max(mt, n) * kp);
+        // evaluation buffers persist across calls (no cudaMalloc/cudaFree on the hot path)
+        DevBuf<T> &Pva = ev_Pva, &Qva = ev_Qva, &at = ev_at, &bt = ev_bt, &t1 = ev_t1, &t2 = ev_t2;
+        Pva.ensure(mt * Kc);
+        Qva.ensure(n * Kc);
+        at.ensure(mt); bt.ensure(n);
+        OC_CUDA(cudaMemsetAsync(at.p, 0, mt * sizeof(T), st));
+        OC_CUDA(cudaMemsetAsync(bt.p, 0, n * sizeof(T), st));
+        t1.ensure(std::max(mt, n) * kp);
+        t2.ensure(std::max(mt, n) * kp);
         for (auto &bk : blocks) {           // ffm.cpp:932-963
             if (!bk.exists) continue;
             if (!bk.side) {

@@ -247,3 +247,77 @@ def csc_of(lab: Labels, n_rows_other: int) -> Tuple[np.ndarray, np.ndarray]:
     colptr = np.zeros(n_rows_other + 1, dtype=np.uint64)
     colptr[1:] = np.cumsum(np.bincount(items, minlength=n_rows_other))
     return colptr, users[order].astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------
+# weak-scaling sets: the item side is fixed, users come in independent seeded blocks of the
+# shape's m rows each (one block per GPU), so ranks can generate their blocks in parallel
+# ---------------------------------------------------------------------------------------
+def _item_side(shape: str, seed: int):
+    cfg = SHAPES[shape]
+    rng = np.random.default_rng([seed, 31337])
+    n = cfg["n"]
+    items = Side(n, [_gen_field(rng, n, dataclasses.replace(s, D=n if s.id_like else s.D)) for s in cfg["fv"]])
+    return items, rng.permutation(n)
+
+
+def user_block(shape: str, seed: int, block: int, n_blocks: int, zipf: float = 1.3):
+    """Users [block*m, (block+1)*m) of an n_blocks*m-user set: (Side, Labels) with global ids."""
+    cfg = SHAPES[shape]
+    m, n = cfg["m"], cfg["n"]
+    _, perm = _item_side(shape, seed)
+    rng = np.random.default_rng([seed, 7919, block])
+    fields = []
+    for s in cfg["fu"]:
+        if s.id_like:
+            fld = Field(m * n_blocks, np.arange(m + 1, dtype=np.uint64),
+                        (np.arange(m, dtype=np.uint64) + block * m).astype(np.uint32), np.ones(m))
+        else:
+            fld = _gen_field(rng, m, s)
+        fields.append(fld)
+    labels = _gen_labels(rng, m, n, cfg["pos"], zipf, perm, cfg.get("min_pos", 0))
+    return Side(m, fields), labels
+
+
+def assemble_blocks(shape: str, seed: int, blocks, test_rows: int = 0, zipf: float = 1.3) -> Dataset:
+    """Concatenate user blocks (in block order) over the shared item side."""
+    cfg = SHAPES[shape]
+    items, perm = _item_side(shape, seed)
+    n = cfg["n"]
+    sides, labs = [b[0] for b in blocks], [b[1] for b in blocks]
+    m = sum(s.rows for s in sides)
+
+    def cat_ptr(ptrs):
+        out, base = [np.zeros(1, dtype=np.uint64)], 0
+        for p in ptrs:
+            out.append(p[1:].astype(np.uint64) + np.uint64(base))
+            base += int(p[-1])
+        return np.concatenate(out)
+
+    fields = []
+    for fi in range(len(cfg["fu"])):
+        fl = [s.fields[fi] for s in sides]
+        fields.append(Field(max(f.D for f in fl), cat_ptr([f.rowptr for f in fl]),
+                            np.concatenate([f.idx for f in fl]), np.concatenate([f.val for f in fl])))
+    users = Side(m, fields)
+    train = Labels(m, max(l.n_items for l in labs), cat_ptr([l.rowptr for l in labs]),
+                   np.concatenate([l.idx for l in labs]))
+    ds = Dataset(shape, users, items, train,
+                 meta=dict(shape=shape, seed=seed, blocks=len(blocks), zipf=zipf, m=m, n=n,
+                           nnz_y=int(train.idx.size)))
+    if test_rows:
+        rng = np.random.default_rng([seed, 104729])
+        tfields = []
+        for s, trained in zip(cfg["fu"], users.fields):
+            spec = dataclasses.replace(s, D=trained.D)
+            if s.id_like:
+                ids = rng.integers(0, trained.D, size=test_rows, dtype=np.int64).astype(np.uint32)
+                fld = Field(trained.D, np.arange(test_rows + 1, dtype=np.uint64), ids, np.ones(test_rows))
+            else:
+                fld = _gen_field(rng, test_rows, spec)
+                fld.idx = np.minimum(fld.idx, np.uint32(trained.D - 1))
+            tfields.append(fld)
+        ds.test_users = Side(test_rows, tfields)
+        ds.test = _gen_labels(rng, test_rows, n, 10.0, zipf, perm, 1)
+        ds.meta.update(test_rows=test_rows)
+    return ds
