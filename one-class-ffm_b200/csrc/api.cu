@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -199,7 +200,10 @@ struct Problem final : CtxBase {
     Omega YU, YV;
     DevBuf<uint32_t> t_rowptr, t_idx, topk_ids, cold_ids, part_id;
     DevBuf<T> part_score, ev_Pva, ev_Qva, ev_at, ev_bt, ev_t1, ev_t2;
+    DevBuf<float> tc_phi, tc_plo, tc_qhi, tc_qlo, tc_cand_score;
+    DevBuf<uint32_t> tc_cand_id;
     bool cold_ready = false;
+    bool eval_tc = true;   // OCFFM_EVAL_TC=0 forces the SIMT scorer
     DevBuf<uint8_t> t_cold;
     std::vector<uint8_t> h_cold;
     bool test_set = false;
@@ -255,6 +259,7 @@ struct Problem final : CtxBase {
                 if (!bk.side) bk.pair = int(f1 * fv + (f2 - fu));
             }
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
+        if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
         a.zero(st); b.zero(st); sa.zero(st); sb.zero(st);
@@ -991,11 +996,34 @@ struct Problem final : CtxBase {
             vector_topk<T>(popular.p, uint32_t(n_ranked), cold_ids.p, st);
             cold_ready = true;
         }
-        const uint32_t nsplit = score_topk_splits(t_row1 - t_row0, uint32_t(n_ranked));
-        part_score.ensure(size_t(mt) * nsplit * 80);
-        part_id.ensure(size_t(mt) * nsplit * 80);
-        score_topk<T>(Pva.p, Qva.p, Kc, bt.p, t_row0, t_row1, uint32_t(n_ranked), t_cold.p, nsplit,
-                      part_score.p, part_id.p, topk_ids.p, st);
+        bool used_tc = false;
+        if constexpr (std::is_same<T, float>::value) {
+            if (eval_tc && score_topk_tc_supported(Kc)) {
+                // tcgen05 path: 3xTF32 operands (hi, lo) of both sides, then the fused scorer
+                const uint32_t nsplit = score_topk_tc_splits(t_row1 - t_row0, uint32_t(n_ranked));
+                tc_phi.ensure(mt * Kc); tc_plo.ensure(mt * Kc);
+                tc_qhi.ensure(n * Kc);  tc_qlo.ensure(n * Kc);
+                split_tf32(Pva.p, tc_phi.p, tc_plo.p, mt * Kc, st);
+                split_tf32(Qva.p, tc_qhi.p, tc_qlo.p, n * Kc, st);
+                const size_t slots = size_t(mt) * nsplit * score_topk_tc_cand_slots();
+                tc_cand_score.ensure(slots);
+                tc_cand_id.ensure(slots);
+                part_score.ensure(size_t(mt) * nsplit * 80);
+                part_id.ensure(size_t(mt) * nsplit * 80);
+                score_topk_tc(tc_phi.p, tc_plo.p, mt, tc_qhi.p, tc_qlo.p, n, Kc, bt.p, t_row0, t_row1,
+                              uint32_t(n_ranked), t_cold.p, nsplit, tc_cand_score.p, tc_cand_id.p,
+                              part_score.p, part_id.p, st);
+                merge_topk<float>(part_score.p, part_id.p, nsplit, t_row0, t_row1, topk_ids.p, st);
+                used_tc = true;
+            }
+        }
+        if (!used_tc) {
+            const uint32_t nsplit = score_topk_splits(t_row1 - t_row0, uint32_t(n_ranked));
+            part_score.ensure(size_t(mt) * nsplit * 80);
+            part_id.ensure(size_t(mt) * nsplit * 80);
+            score_topk<T>(Pva.p, Qva.p, Kc, bt.p, t_row0, t_row1, uint32_t(n_ranked), t_cold.p, nsplit,
+                          part_score.p, part_id.p, topk_ids.p, st);
+        }
         acc64.zero(st);
         eval_metrics<T>(topk_ids.p, cold_ids.p, t_cold.p, t_rowptr.p, t_idx.p, t_row0, t_row1, Pva.p,
                         Qva.p, Kc, at.p, bt.p, popular.p, uint32_t(n), uint32_t(n_ranked), acc64.p, st);

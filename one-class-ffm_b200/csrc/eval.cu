@@ -396,6 +396,13 @@ void score_topk(const T *Pva, const T *Qva, uint32_t Kc, const T *bt, uint32_t r
     const dim3 grid(unsigned((uint64_t(row1 - row0) + TU - 1) / TU), nsplit);
     OC_LAUNCH((k_score_topk<T>), grid, kThreads, smem, s, Pva, Qva, Kc, bt, row0, row1, n_ranked, per,
               nsplit, cold, part_score, part_id);
+    merge_topk<T>(part_score, part_id, nsplit, row0, row1, ids, s);
+}
+
+template <typename T>
+void merge_topk(const T *part_score, const uint32_t *part_id, uint32_t nsplit, uint32_t row0,
+                uint32_t row1, uint32_t *ids, cudaStream_t s) {
+    if (row1 <= row0) return;
     const unsigned blocks = unsigned((uint64_t(row1 - row0) * 32 + kThreads - 1) / kThreads);
     OC_LAUNCH((k_merge_topk<T>), blocks, kThreads, 0, s, part_score, part_id, nsplit, row0, row1, ids);
 }
@@ -423,6 +430,8 @@ void eval_metrics(const uint32_t *ids, const uint32_t *cold_ids80, const uint8_t
                                 uint32_t, const uint8_t *, uint32_t, T *, uint32_t *, uint32_t *,  \
                                 cudaStream_t);                                                     \
     template void vector_topk<T>(const T *, uint32_t, uint32_t *, cudaStream_t);                   \
+    template void merge_topk<T>(const T *, const uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t *, \
+                                cudaStream_t);                                                     \
     template void eval_metrics<T>(const uint32_t *, const uint32_t *, const uint8_t *,             \
                                   const uint32_t *, const uint32_t *, uint32_t, uint32_t,          \
                                   const T *, const T *, uint32_t, const T *, const T *, const T *, \

@@ -168,6 +168,21 @@ template <typename T>
 void score_topk(const T *Pva, const T *Qva, uint32_t Kc, const T *bt, uint32_t row0, uint32_t row1,
                 uint32_t n_ranked, const uint8_t *cold, uint32_t nsplit, T *part_score,
                 uint32_t *part_id, uint32_t *ids, cudaStream_t s);
+// merge of the per-item-range partial lists (also used behind the tensor-core scorer)
+template <typename T>
+void merge_topk(const T *part_score, const uint32_t *part_id, uint32_t nsplit, uint32_t row0,
+                uint32_t row1, uint32_t *ids, cudaStream_t s);
+
+// ---- eval_tc.cu (fp32 contexts): tcgen05 3xTF32 scorer -------------------------------------------
+bool score_topk_tc_supported(uint32_t Kc);
+size_t score_topk_tc_cand_slots();
+uint32_t score_topk_tc_splits(uint32_t rows, uint32_t n_ranked);
+void split_tf32(const float *x, float *hi, float *lo, uint64_t n, cudaStream_t s);
+void score_topk_tc(const float *Phi, const float *Plo, uint64_t p_rows, const float *Qhi, const float *Qlo,
+                   uint64_t q_rows, uint32_t Kc, const float *bt, uint32_t row0, uint32_t row1,
+                   uint32_t n_ranked, const uint8_t *cold, uint32_t nsplit, float *cand_score,
+                   uint32_t *cand_id, float *part_score, uint32_t *part_id, cudaStream_t s);
+
 // top-80 of a plain score vector (the `popular` ranking shared by all cold rows)
 template <typename T>
 void vector_topk(const T *z, uint32_t n_ranked, uint32_t *ids80, cudaStream_t s);
