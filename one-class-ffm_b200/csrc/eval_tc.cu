@@ -27,7 +27,9 @@ namespace {
 constexpr int TOP = 80;
 constexpr int TM = 128, TN = 128, BK = 32;          // tile rows, tile items, floats per K-block
 constexpr int STAGES = 3;
+constexpr int NACC = 4;                             // TMEM accumulators (4 x 128 = all 512 columns)
 constexpr int CAP = 256;                            // candidate slots per (row, item range)
+constexpr int KPL = CAP / 32;                       // sort keys per lane
 constexpr uint32_t STAGE_BYTES = 4u * (TM * BK * 4u);   // A_hi, A_lo, B_hi, B_lo
 constexpr int kThreadsTC = 192;
 
@@ -115,15 +117,15 @@ __device__ __forceinline__ float key_score(uint64_t k) {
 }
 __device__ __forceinline__ uint32_t key_id(uint64_t k) { return ~uint32_t(k); }
 
-// Warp-cooperative compaction of one row's candidate buffer (count <= CAP = 256) to its exact
-// top-80 in (score desc, id asc) order: an in-register bitonic sort of 8 keys per lane (element
+// Warp-cooperative compaction of one row's candidate buffer (count <= CAP) to its exact top-80 in
+// (score desc, id asc) order: an in-register bitonic sort of KPL keys per lane (element
 // e = r*32 + lane), fully unrolled so every register index is static.  The sorted survivors are
 // written back to the front of the buffer; returns their number, *th = the 80th score if full.
 __device__ __noinline__ int compact_row(float *cs, uint32_t *ci, int count, float *th) {
     const int lane = threadIdx.x & 31;
-    uint64_t key[8];
+    uint64_t key[KPL];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < KPL; ++r) {
         const int e = r * 32 + lane;
         key[r] = e < count ? pack_key(cs[e], ci[e]) : 0ull;
     }
@@ -134,7 +136,7 @@ __device__ __noinline__ int compact_row(float *cs, uint32_t *ci, int count, floa
             if (j >= 32) {
                 const int dr = j >> 5;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < KPL; ++r) {
                     if ((r & dr) == 0) {
                         const bool desc = ((r * 32) & k) == 0;      // lane bits are below k here
                         const uint64_t a = key[r], b = key[r | dr];
@@ -145,7 +147,7 @@ __device__ __noinline__ int compact_row(float *cs, uint32_t *ci, int count, floa
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < KPL; ++r) {
                     const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
                     const int e = r * 32 + lane;
                     const bool desc = (e & k) == 0;
@@ -170,16 +172,42 @@ __device__ __noinline__ int compact_row(float *cs, uint32_t *ci, int count, floa
     return n;
 }
 
-struct SmemTC {
+// v[c] for a run-time c without putting v[] into local memory
+__device__ __forceinline__ float pick32(const float (&v)[32], int c) {
+    float x = v[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) x = (c == i) ? v[i] : x;
+    return x;
+}
+
+// Two shared-memory plans.  Streaming: A and B K-blocks share a 3-stage ring (any Kc).
+// Resident (Kc <= 128): the CTA's A tile (hi + lo, all K-blocks, 128 KB) is loaded once and only
+// B streams through the ring -- half the L2->SM operand traffic, which is what bounds this kernel.
+constexpr int MAX_RES_KB = 4;
+template <bool RESA>
+struct SmemTC;
+template <>
+struct SmemTC<false> {
     float a_hi[STAGES][TM * BK];
     float a_lo[STAGES][TM * BK];
     float b_hi[STAGES][TN * BK];
     float b_lo[STAGES][TN * BK];
-    float bias[2][TN];
-    uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+    __align__(16) float bias[4][32];   // one private 32-column slice per epilogue warp: no cross-warp barrier
+    uint64_t full[STAGES], empty[STAGES], tfull[NACC], tempty[NACC], afull;
+    uint32_t tmem_base;
+};
+template <>
+struct SmemTC<true> {
+    float a_hi[MAX_RES_KB][TM * BK];
+    float a_lo[MAX_RES_KB][TM * BK];
+    float b_hi[STAGES][TN * BK];
+    float b_lo[STAGES][TN * BK];
+    __align__(16) float bias[4][32];   // one private 32-column slice per epilogue warp: no cross-warp barrier
+    uint64_t full[STAGES], empty[STAGES], tfull[NACC], tempty[NACC], afull;
     uint32_t tmem_base;
 };
 
+template <bool RESA>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -190,7 +218,8 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles must start on 1024-byte boundaries of the shared window
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
-    SmemTC &sm = *reinterpret_cast<SmemTC *>(smem_raw + pad);
+    SmemTC<RESA> &sm = *reinterpret_cast<SmemTC<RESA> *>(smem_raw + pad);
+    constexpr uint32_t kStageBytes = RESA ? 2u * (TN * BK * 4u) : STAGE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t u0 = row0 + blockIdx.x * TM;
     const uint32_t j_lo = blockIdx.y * items_per_split;
@@ -200,12 +229,13 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 4); }
+        for (int s = 0; s < NACC; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 4); }
+        mbar_init(&sm.afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
-                     "r"(256u)
+                     "r"(uint32_t(NACC * TN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -217,15 +247,24 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            if (RESA && ntiles) {
+                mbar_expect_tx(&sm.afull, nkb * 2u * (TM * BK * 4u));
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    tma_load_2d(sm.a_hi[kb], &map_a_hi, &sm.afull, int(kb * BK), int(u0));
+                    tma_load_2d(sm.a_lo[kb], &map_a_lo, &sm.afull, int(kb * BK), int(u0));
+                }
+            }
             uint32_t it = 0;
             for (uint32_t t = 0; t < ntiles; ++t) {
                 const int j0 = int(j_lo + t * TN);
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&sm.empty[s], ph ^ 1u);
-                    mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-                    tma_load_2d(sm.a_hi[s], &map_a_hi, &sm.full[s], int(kb * BK), int(u0));
-                    tma_load_2d(sm.a_lo[s], &map_a_lo, &sm.full[s], int(kb * BK), int(u0));
+                    mbar_expect_tx(&sm.full[s], kStageBytes);
+                    if (!RESA) {
+                        tma_load_2d(sm.a_hi[s], &map_a_hi, &sm.full[s], int(kb * BK), int(u0));
+                        tma_load_2d(sm.a_lo[s], &map_a_lo, &sm.full[s], int(kb * BK), int(u0));
+                    }
                     tma_load_2d(sm.b_hi[s], &map_b_hi, &sm.full[s], int(kb * BK), j0);
                     tma_load_2d(sm.b_lo[s], &map_b_lo, &sm.full[s], int(kb * BK), j0);
                 }
@@ -234,9 +273,10 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
+            if (RESA && ntiles) mbar_wait(&sm.afull, 0);
             uint32_t it = 0;
             for (uint32_t t = 0; t < ntiles; ++t) {
-                const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+                const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
                 mbar_wait(&sm.tempty[acc], aph ^ 1u);     // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + acc * TN;
@@ -244,7 +284,8 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&sm.full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t ah = make_desc(sm.a_hi[s]), al = make_desc(sm.a_lo[s]);
+                    const uint32_t as = RESA ? kb : s;
+                    const uint64_t ah = make_desc(sm.a_hi[as]), al = make_desc(sm.a_lo[as]);
                     const uint64_t bh = make_desc(sm.b_hi[s]), bl = make_desc(sm.b_lo[s]);
 #pragma unroll
                     for (uint32_t k = 0; k < BK / 8; ++k) {
@@ -267,49 +308,68 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         float *cs = cand_score + slot * CAP;
         uint32_t *ci = cand_id + slot * CAP;
         int count = 0;
-        float th = live ? -INFINITY : INFINITY;
+        float th = live ? -3.0e38f : INFINITY;   // finite floor: -inf (out-of-range columns) never passes
         for (uint32_t t = 0; t < ntiles; ++t) {
-            const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+            const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             const uint32_t j0 = j_lo + t * TN;
-            // item bias of this tile (each epilogue warp loads a quarter), double buffered by acc
-            {
-                const uint32_t j = j0 + uint32_t(ew) * 32u + uint32_t(lane);
-                sm.bias[acc][ew * 32 + lane] = j < j_hi ? bt[j] : 0.f;
-            }
-            // make room: a tile can add at most TN candidates to a row
-            uint32_t need = __ballot_sync(0xffffffffu, count > CAP - TN);
-            while (need) {
-                const int l = __ffs(need) - 1;
-                need &= need - 1;
-                float *rcs = reinterpret_cast<float *>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(cs), l));
-                uint32_t *rci = reinterpret_cast<uint32_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ci), l));
-                const int rc = __shfl_sync(0xffffffffu, count, l);
-                float nth = -INFINITY;
-                const int n = compact_row(rcs, rci, rc, &nth);
-                if (lane == l) {
-                    count = n;
-                    if (n == TOP) th = nth;
-                }
-                __syncwarp();
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // bias tile visible to the 4 epilogue warps
             mbar_wait(&sm.tfull[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + acc * TN + (uint32_t(q * 32) << 16);
+            float bnext;   // item bias of the next 32 columns, fetched one chunk ahead
+            {
+                const uint32_t j = j0 + uint32_t(lane);
+                bnext = j < j_hi ? bt[j] : -INFINITY;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < TN; c0 += 32) {
+                // make room: a chunk can add at most 32 candidates to a row
+                uint32_t need = __ballot_sync(0xffffffffu, count > CAP - 32);
+                while (need) {
+                    const int l = __ffs(need) - 1;
+                    need &= need - 1;
+                    float *rcs = reinterpret_cast<float *>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(cs), l));
+                    uint32_t *rci = reinterpret_cast<uint32_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ci), l));
+                    const int rc = __shfl_sync(0xffffffffu, count, l);
+                    float nth = -3.0e38f;
+                    const int n = compact_row(rcs, rci, rc, &nth);
+                    if (lane == l) {
+                        count = n;
+                        if (n == TOP) th = nth;
+                    }
+                    __syncwarp();
+                }
+                __syncwarp();
+                sm.bias[ew][lane] = bnext;   // -inf past the item range: such a column can never pass
+                __syncwarp();
+                if (c0 + 32 < TN) {
+                    const uint32_t j = j0 + uint32_t(c0 + 32 + lane);
+                    bnext = j < j_hi ? bt[j] : -INFINITY;
+                }
                 uint32_t r[32];
                 tmem_ld32(taddr + uint32_t(c0), r);
+                float v[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float v = __uint_as_float(r[c]) + sm.bias[acc][c0 + c];
-                    const uint32_t j = j0 + uint32_t(c0 + c);
-                    if (v >= th && j < j_hi) {
-                        cs[count] = v;
-                        ci[count] = j;
-                        ++count;
-                    }
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(&sm.bias[ew][c]);
+                    v[c + 0] = __uint_as_float(r[c + 0]) + b4.x;
+                    v[c + 1] = __uint_as_float(r[c + 1]) + b4.y;
+                    v[c + 2] = __uint_as_float(r[c + 2]) + b4.z;
+                    v[c + 3] = __uint_as_float(r[c + 3]) + b4.w;
                 }
+                // branch-free filter: one compare + one predicated OR per column builds the lane's
+                // mask of passing columns; the (per lane) rare appends are done afterwards
+                uint32_t m = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (v[c] >= th) m |= 1u << c;
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    cs[count] = pick32(v, c);
+                    ci[count] = j0 + uint32_t(c0 + c);
+                    ++count;
+                }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -336,7 +396,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(NACC * TN)) : "memory");
     }
 }
 
@@ -407,13 +467,20 @@ void score_topk_tc(const float *Phi, const float *Plo, uint64_t p_rows, const fl
     if (row1 <= row0) return;
     const CUtensorMap ma_hi = make_map(Phi, p_rows, Kc), ma_lo = make_map(Plo, p_rows, Kc);
     const CUtensorMap mb_hi = make_map(Qhi, q_rows, Kc), mb_lo = make_map(Qlo, q_rows, Kc);
-    const size_t smem = sizeof(SmemTC) + 1024;
-    OC_CUDA(cudaFuncSetAttribute(k_score_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     const uint32_t item_tiles = (n_ranked + TN - 1) / TN;
     const uint32_t per = ((item_tiles + nsplit - 1) / nsplit) * TN;
     const dim3 grid(unsigned((uint64_t(row1 - row0) + TM - 1) / TM), nsplit);
-    OC_LAUNCH(k_score_topk_tc, grid, kThreadsTC, smem, s, ma_hi, ma_lo, mb_hi, mb_lo, Kc, bt, row0, row1,
-              n_ranked, per, nsplit, cold, cand_score, cand_id, part_score, part_id);
+    if (Kc / BK <= MAX_RES_KB) {
+        const size_t smem = sizeof(SmemTC<true>) + 1024;
+        OC_CUDA(cudaFuncSetAttribute(k_score_topk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        OC_LAUNCH(k_score_topk_tc<true>, grid, kThreadsTC, smem, s, ma_hi, ma_lo, mb_hi, mb_lo, Kc, bt, row0, row1,
+                  n_ranked, per, nsplit, cold, cand_score, cand_id, part_score, part_id);
+    } else {
+        const size_t smem = sizeof(SmemTC<false>) + 1024;
+        OC_CUDA(cudaFuncSetAttribute(k_score_topk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        OC_LAUNCH(k_score_topk_tc<false>, grid, kThreadsTC, smem, s, ma_hi, ma_lo, mb_hi, mb_lo, Kc, bt, row0, row1,
+                  n_ranked, per, nsplit, cold, cand_score, cand_id, part_score, part_id);
+    }
 }
 
 }  // namespace ocffm
