@@ -46,8 +46,9 @@ def peaks():
     if os.path.exists(path):
         with open(path) as fh:
             d = json.load(fh)
-        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops", 1590.0)),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler(threading.Thread):
@@ -266,9 +267,14 @@ def main():
     objective = prob.objective()
 
     pk = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_hv_traffic.json")
+    if args.workload == "C2" and world == 1 and os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh)["traffic_bytes_per_launch_avg"]   # ncu dram read+write per launch
     hv_gbs = (st.hv_algo_bytes / 1e9) / (st.hv_ms / 1e3) if st.hv_ms > 0 else None
     roofline = dict(bound="hbm", kernel="k_hess_cross (hs_cross row pass)", achieved=hv_gbs, peak=pk["hbm_gbs"],
-                    unit="GB/s", frac=(hv_gbs / pk["hbm_gbs"]) if hv_gbs else None, traffic=None,
+                    unit="GB/s", frac=(hv_gbs / pk["hbm_gbs"]) if hv_gbs else None, traffic=traffic,
                     peak_source=pk["source"], launches=int(st.hv_launches),
                     avg_launch_ms=(st.hv_ms / st.hv_launches) if st.hv_launches else None,
                     share_of_step=(st.hv_ms / ms) if ms > 0 else None,
@@ -289,8 +295,19 @@ def main():
         ems = dist_util.max_over_ranks(ems)
         fx = ds.users.f * ds.items.f
         flops = 2.0 * ds.test.rows * ds.train.n_items * fx * k
+        # tensor roofline of the scorer: 3xTF32 issues 3 MMAs per algorithmic MAC; TF32 dense peak is
+        # taken as half of the measured bf16 burst figure
+        tf32_peak = pk["bf16_tflops"] / 2.0
+        alg_tflops = flops / (ems / 1e3) / 1e12
         eval_info = dict(users_per_s=ds.test.rows / (ems / 1e3), ms=ems, m_t=ds.test.rows,
-                         n_ranked=ds.train.n_items, tflops=flops / (ems / 1e3) / 1e12,
+                         n_ranked=ds.train.n_items, tflops=alg_tflops,
+                         roofline=dict(bound="tensor", kernel="k_score_topk_tc (tcgen05 kind::tf32, 3xTF32)"
+                                       if args.dtype == "f32" else "k_score_topk (SIMT)",
+                                       achieved=3.0 * alg_tflops if args.dtype == "f32" else alg_tflops,
+                                       peak=tf32_peak, unit="TFLOP/s",
+                                       frac=(3.0 * alg_tflops if args.dtype == "f32" else alg_tflops) / tf32_peak,
+                                       note="whole validate() timed (SpMM, TF32 split, scorer, merge, metrics); "
+                                            "achieved counts the 3 TF32 MMAs per algorithmic MAC"),
                          p_at_10=float(res["prec"][1]), ndcg_at_10=float(res["ndcg"][1]), ploss=float(res["ploss"]))
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
