@@ -166,16 +166,23 @@ struct Problem final : CtxBase {
     cudaStream_t st = nullptr;
     Comm comm;
     uint32_t chunk = 64;
+    uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
     bool profile = false;
 
     struct Field {
         bool set = false;
         uint64_t rows = 0, D = 0, nnz = 0;
-        DevBuf<uint32_t> rowptr, idx;
-        DevBuf<T> val, freq;
+        DevBuf<uint32_t> rowptr, idx, hot_feat;
+        DevBuf<T> val, freq, shadow;
+        DevBuf<int16_t> hot_slot;
+        uint32_t n_hot = 0;
         uint32_t row0 = 0, row1 = 0;
-        CsrView<T> view() const { return {rowptr.p, idx.p, val.p, row0, row1}; }
-        CsrView<T> view_all() const { return {rowptr.p, idx.p, val.p, 0, uint32_t(rows)}; }
+        CsrView<T> view() const {
+            return {rowptr.p, idx.p, val.p, row0, row1, n_hot ? hot_slot.p : nullptr, shadow.p};
+        }
+        CsrView<T> view_all() const {
+            return {rowptr.p, idx.p, val.p, 0, uint32_t(rows), n_hot ? hot_slot.p : nullptr, shadow.p};
+        }
     };
     struct Omega {
         bool set = false;
@@ -260,6 +267,7 @@ struct Problem final : CtxBase {
             }
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
         if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
         a.zero(st); b.zero(st); sa.zero(st); sb.zero(st);
@@ -336,6 +344,25 @@ struct Problem final : CtxBase {
         F.idx.upload(idx, nnz, st);
         F.val.upload(v, st);
         F.freq.upload(fr, st);
+        // hot features: those hit by >= hot_min scatter contributions per pass (at most 1024,
+        // the most frequent first); they get kHotReplicas shadow rows each (kernels.h CsrView)
+        F.n_hot = 0;
+        if (side != OCFFM_SIDE_T && hot_min > 0) {
+            std::vector<std::pair<T, uint32_t>> cand;
+            for (uint64_t d = 0; d < D; ++d)
+                if (fr[d] >= T(hot_min)) cand.emplace_back(fr[d], uint32_t(d));
+            std::sort(cand.begin(), cand.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
+            if (cand.size() > 1024) cand.resize(1024);
+            if (!cand.empty()) {
+                std::vector<int16_t> slot(D, int16_t(-1));
+                std::vector<uint32_t> feat(cand.size());
+                for (size_t i = 0; i < cand.size(); ++i) { slot[cand[i].second] = int16_t(i); feat[i] = cand[i].second; }
+                F.hot_slot.upload(slot, st);
+                F.hot_feat.upload(feat, st);
+                F.shadow.alloc(cand.size() * size_t(kHotReplicas) * kp);
+                F.n_hot = uint32_t(cand.size());
+            }
+        }
         F.row0 = lo(rows);
         F.row1 = hi(rows);
         F.set = true;
@@ -637,6 +664,7 @@ struct Problem final : CtxBase {
     void grad_scatter(const Half &h) {
         const size_t s = sizeof(T);
         OC_CUDA(cudaMemsetAsync(G.p, 0, h.D * kp * sizeof(T), st));
+        if (h.X->n_hot) h.X->shadow.zero(st);
         const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
         if (h.side) {
             OC_CUDA(cudaMemsetAsync(ysum.p, 0, h.m1 * sizeof(T), st));
@@ -656,6 +684,7 @@ struct Problem final : CtxBase {
             algo_bytes += (h.m1 + 1) * 8 + nnzY * (4 + s) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
                           uint64_t(Fx) * h.m1 * k * s + h.m1 * s + nnzX * (4 + s) + 2 * h.D * k * s;
         }
+        if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, G.p, kp, st);
         comm.allreduce(G.p, h.D * kp, st);
         nnz_trav += nnzY + nnzX;
     }
@@ -680,6 +709,7 @@ struct Problem final : CtxBase {
     // Hv (without the regulariser) for the direction in V.  Returns nothing; the caller accounts
     // the statistics with account_hess() once it knows the iteration really ran.
     void hess_scatter(const Half &h, Gate gate) {
+        if (h.X->n_hot) h.X->shadow.zero(st);
         if (h.side) {
             side_rows<T>(1, h.Yown->view(), h.X->view(), h.Q1, nullptr, nullptr, nullptr, nullptr, V.p,
                          T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, gate, st);
@@ -695,6 +725,7 @@ struct Problem final : CtxBase {
                                kp, gate, st);
             if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
         }
+        if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, Hv.p, kp, st);
         comm.allreduce(Hv.p, h.D * kp, st);
     }
     void account_hess(const Half &h, uint64_t iters) {
@@ -771,8 +802,6 @@ struct Problem final : CtxBase {
             spmm_rows<T>(h.X->view(), S.p, XS.p, kp, kp, st);
             comm.allgather_rows(XS.p, h.m1, kp, st);
             // P1 += XS (and the side terms) on every rank's replica
-            CsrView<T> none{nullptr, nullptr, nullptr, 0, 0};
-            (void)none;
             spmm_update_from_xs(h, q_side);
         }
         if (h.side) {

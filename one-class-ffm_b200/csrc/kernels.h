@@ -15,7 +15,14 @@ struct CsrView {
     const uint32_t *idx;     // [nnz]
     const T *val;            // [nnz]
     uint32_t row0, row1;     // rows owned by this rank (global row ids)
+    // Hot features (skewed fields): X^T(.) contributions to feature f with hot_slot[f] >= 0 go to
+    // one of kHotReplicas shadow rows (picked by warp) instead of the single row of G / Hv, so
+    // the REDs of a feature that occurs millions of times do not serialise on one L2 address;
+    // fold_hot() adds the replicas back.  Null when the field has no hot feature.
+    const int16_t *hot_slot; // [D] or nullptr
+    T *shadow;               // [n_hot * kHotReplicas * kp]
 };
+constexpr int kHotReplicas = 64;
 
 // The observed pairs Omega in one orientation (U->Y by user or V->Y by item) cut into bounded
 // work items so that power-law rows cannot serialise a warp: item w covers nnz
@@ -104,6 +111,10 @@ void ytilde_add_gap(const OmegaView<T> &Y, const T *gap, int by_row, cudaStream_
 template <typename T>
 void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accumulate,
                  cudaStream_t s);
+
+// Out[hot_feat[s], :] += sum_r shadow[(s * kHotReplicas + r), :]  (see CsrView::hot_slot)
+template <typename T>
+void fold_hot(const T *shadow, const uint32_t *hot_feat, uint32_t n_hot, T *Out, int kp, cudaStream_t s);
 
 // ---- dense.cu --------------------------------------------------------------------------------
 // Out64[Kc x kp] += A[rows x Kc]^T B[rows x kp]; colsum64[0:kp] += B^T 1 ; wsum64[0:kp] += B^T wvec

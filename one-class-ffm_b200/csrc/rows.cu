@@ -15,6 +15,9 @@ namespace ocffm {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef OC_GATHER_MINB
+#define OC_GATHER_MINB 1
+#endif
 
 template <int G>
 __device__ __forceinline__ uint32_t group_mask() {
@@ -31,6 +34,19 @@ __device__ __forceinline__ T gsum(T v, uint32_t mask) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
+}
+
+// destination row of a scatter contribution to feature `idx` (hot features: a per-warp replica)
+template <typename T>
+__device__ __forceinline__ T *scatter_row(const CsrView<T> &X, T *Out, uint32_t idx, uint32_t kp) {
+    if (X.hot_slot) {
+        const int hs = X.hot_slot[idx];
+        if (hs >= 0) {
+            const uint32_t rep = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) & (kHotReplicas - 1);
+            return X.shadow + (size_t(hs) * kHotReplicas + rep) * kp;
+        }
+    }
+    return Out + size_t(idx) * kp;
 }
 
 template <typename T>
@@ -84,7 +100,7 @@ k_spmm_update(CsrView<T> X, const T *__restrict__ S, T *__restrict__ XS, T *__re
 
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
              const T *__restrict__ Tm, const T *__restrict__ a1, const T *__restrict__ oQ,
              const T *__restrict__ bQ, T w, T r, T *__restrict__ Gout) {
@@ -132,11 +148,11 @@ k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
     }
     const uint32_t e = X.rowptr[row + 1];
     for (uint32_t t = X.rowptr[row]; t < e; ++t)
-        red4(Gout + size_t(X.idx[t]) * kp + lg * 4, scale4(pk, X.val[t]));
+        red4(scatter_row(X, Gout, X.idx[t], kp) + lg * 4, scale4(pk, X.val[t]));
 }
 
 template <typename T, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
              const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate) {
     constexpr uint32_t kp = 4 * G;
@@ -186,11 +202,11 @@ k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
     V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
                omw * ka.w + w * tau.w};
     for (uint32_t t = xb; t < xe; ++t)
-        red4(Hv + size_t(X.idx[t]) * kp + lg * 4, scale4(z, X.val[t]));
+        red4(scatter_row(X, Hv, X.idx[t], kp) + lg * 4, scale4(z, X.val[t]));
 }
 
 template <typename T, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *__restrict__ Vo,
             uint32_t ldv) {
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
@@ -275,7 +291,7 @@ k_side_rows(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, const T *__r
         z = gsum<G>(acc, mask) * ((T(1) - w) * cnt + w * n1);
     }
     for (uint32_t t = xb; t < xe; ++t)
-        red4(Out + size_t(X.idx[t]) * kp + lg * 4, scale4(q, X.val[t] * z));
+        red4(scatter_row(X, Out, X.idx[t], kp) + lg * 4, scale4(q, X.val[t] * z));
 }
 
 template <typename T>
@@ -324,6 +340,27 @@ k_rowwise_dot(const T *__restrict__ P, const T *__restrict__ Q, uint32_t rows, T
     const uint32_t mask = group_mask<G>();
     const T d = gsum<G>(dot4(ldg4(P + g * kp + lg * 4), ldg4(Q + g * kp + lg * 4)), mask);
     if (lg == 0) out[g] = accumulate ? out[g] + d : d;
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_fold_hot(const T *__restrict__ shadow, const uint32_t *__restrict__ hot_feat, uint32_t n_hot,
+           T *__restrict__ Out) {
+    constexpr uint32_t kp = 4 * G;
+    const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (g >= n_hot) return;
+    const uint32_t lg = threadIdx.x % G;
+    V4<T> acc = zero4<T>();
+    const T *base = shadow + size_t(g) * kHotReplicas * kp + lg * 4;
+#pragma unroll 8
+    for (int r = 0; r < kHotReplicas; ++r) {
+        const V4<T> v = ld4(base + size_t(r) * kp);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    T *dst = Out + size_t(hot_feat[g]) * kp + lg * 4;
+    V4<T> o = ld4(dst);
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    st4(dst, o);
 }
 
 inline unsigned blocks_for(uint64_t groups, int G) {
@@ -427,6 +464,13 @@ void ytilde_add_gap(const OmegaView<T> &Y, const T *gap, int by_row, cudaStream_
 }
 
 template <typename T>
+void fold_hot(const T *shadow, const uint32_t *hot_feat, uint32_t n_hot, T *Out, int kp, cudaStream_t s) {
+    if (!n_hot) return;
+    OC_DISPATCH_G(kp, OC_LAUNCH((k_fold_hot<T, G>), blocks_for(n_hot, G), kThreads, 0, s, shadow, hot_feat,
+                                n_hot, Out));
+}
+
+template <typename T>
 void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accumulate,
                  cudaStream_t s) {
     if (!rows) return;
@@ -451,7 +495,8 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
                                cudaStream_t);                                                      \
     template void ytilde_base<T>(const OmegaView<T> &, const T *, const T *, cudaStream_t);        \
     template void ytilde_add_gap<T>(const OmegaView<T> &, const T *, int, cudaStream_t);           \
-    template void rowwise_dot<T>(const T *, const T *, uint32_t, int, T *, int, cudaStream_t);
+    template void rowwise_dot<T>(const T *, const T *, uint32_t, int, T *, int, cudaStream_t);     \
+    template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);
 
 OC_INSTANTIATE(float)
 OC_INSTANTIATE(double)

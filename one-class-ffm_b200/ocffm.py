@@ -14,7 +14,7 @@ from typing import Dict, Iterator, Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libocffm_cuda.so")
+LIB_PATH = os.environ.get("OCFFM_LIB", os.path.join(_HERE, "libocffm_cuda.so"))   # OCFFM_LIB: tuning builds only
 F32, F64 = 0, 1
 SIDE_U, SIDE_V, SIDE_T = 0, 1, 2
 TOPK = (5, 10, 20, 40, 80)

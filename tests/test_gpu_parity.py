@@ -182,3 +182,30 @@ def test_against_oracle_on_c1_slice(dt):
     if mism == 0:
         assert rel_err(rp["prec"], ro["prec"]) <= 1e-12 and rel_err(rp["ndcg"], ro["ndcg"]) <= 1e-9
     assert abs(rp["ploss"] - ro["ploss"]) <= 10 * tol * abs(ro["ploss"])
+
+
+def test_hot_feature_shadow_replicas(dt, monkeypatch):
+    """Skewed fields: scatter contributions of hot features go through replicated shadow rows
+    (OCFFM_HOT_MIN lowered so that the small set exercises the path) -- same results."""
+    import importlib
+    synth = importlib.import_module("synth")
+    dtype, tol = DT[dt]
+    monkeypatch.setenv("OCFFM_HOT_MIN", "4")
+    ds = synth.generate("C1", seed=8, scale=0.1, test_rows=50)
+    prm = dict(k=8, lam=2.0, omega=2.0 ** -6, r=-1.0, self_side=True, freq=True)
+    o = pyoracle.Oracle(ds, **prm)
+    p = ocffm.Problem(ds, dtype=dtype, **prm)
+    for (f1, f2, which), w in p.init_model(seed=2).items():
+        o.set_block(f1, f2, which, w)
+    o.init_state()
+    p.init_state()
+    fu = p.fu
+    for (f1, f2, which) in [(1, fu + 1, "W"), (1, fu + 1, "H"), (1, 1, "W"), (fu + 1, fu + 1, "H"), (0, fu, "W")]:
+        G = o.grad(f1, f2, which)
+        assert rel_err(p.grad(f1, f2, which), G) <= tol, (f1, f2, which)
+        assert rel_err(p.hess_vec(f1, f2, which, -G), o.hess_vec(f1, f2, which, -G)) <= tol
+    o.one_epoch()
+    p.one_epoch()
+    if dt == "f64":
+        assert int(p.stats().cg_iters) == o.cg_iters_total()
+        assert abs(p.objective() - o.func()) <= 1e-9 * abs(o.func())
