@@ -497,22 +497,41 @@ struct Problem final : CtxBase {
         h_stage = nullptr;
         OC_CUDA(cudaMallocHost(&h_stage, n_ * sizeof(double)));
         h_stage_n = n_;
-        d_stage.alloc(n_);
     }
-    // fp64 [rows x k] host -> pinned staging -> device -> T [rows x kp] (conversion on the device)
+    static bool is_pinned(const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    }
+    void ensure_dstage(size_t n_) {
+        if (d_stage.n < n_) d_stage.alloc(n_);
+    }
+    // fp64 [rows x k] host -> device -> T [rows x kp] (conversion + zero padding on the device).
+    // Pinned caller buffers are DMA'd directly; pageable ones go through a pinned staging copy.
     void upload_padded(DevBuf<T> &dst, const double *src, uint64_t rows) {
         const size_t cnt = rows * k;
-        ensure_stage(cnt);
-        memcpy(h_stage, src, cnt * sizeof(double));
-        OC_CUDA(cudaMemcpyAsync(d_stage.p, h_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        ensure_dstage(cnt);
+        const double *from = src;
+        if (!is_pinned(src)) {
+            ensure_stage(cnt);
+            memcpy(h_stage, src, cnt * sizeof(double));
+            from = h_stage;
+        }
+        OC_CUDA(cudaMemcpyAsync(d_stage.p, from, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
         dst.ensure(rows * kp);
         pad_from_f64<T>(d_stage.p, dst.p, rows, k, kp, st);
         sync();
     }
     void download_unpadded(const T *src, uint64_t ld, double *dst, uint64_t rows) {
         const size_t cnt = rows * k;
-        ensure_stage(cnt);
+        ensure_dstage(cnt);
         unpad_to_f64<T>(src, uint32_t(ld), d_stage.p, rows, k, st);
+        if (is_pinned(dst)) {
+            OC_CUDA(cudaMemcpyAsync(dst, d_stage.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            sync();
+            return;
+        }
+        ensure_stage(cnt);
         OC_CUDA(cudaMemcpyAsync(h_stage, d_stage.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         sync();
         memcpy(dst, h_stage, cnt * sizeof(double));

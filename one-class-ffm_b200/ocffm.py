@@ -213,14 +213,17 @@ class Problem:
         return self._field(f1 if which == "W" else f2).D
 
     def set_block(self, f1, f2, which, data):
-        d = _f64(data).reshape(-1)
+        d = _f64(data).reshape(-1)   # no copy for a contiguous float64 array (keeps pinned memory pinned)
         rows = self.block_rows(f1, f2, which)
         assert d.size == rows * self.k
         self._ck(self.L.ocffm_set_block(self.h, f1, f2, ord(which), _p(d, C.c_double), rows))
 
-    def get_block(self, f1, f2, which) -> np.ndarray:
+    def get_block(self, f1, f2, which, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`out`: an existing float64 [rows, k] array to fill (e.g. pinned memory for DMA)."""
         rows = self.block_rows(f1, f2, which)
-        out = np.empty((rows, self.k), dtype=np.float64)
+        if out is None:
+            out = np.empty((rows, self.k), dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == rows * self.k and out.flags["C_CONTIGUOUS"]
         self._ck(self.L.ocffm_get_block(self.h, f1, f2, ord(which), _p(out, C.c_double), rows))
         return out
 

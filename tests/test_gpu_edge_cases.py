@@ -1,0 +1,107 @@
+"""Edge cases of the hot path on the GPU: latent sizes that need padding or a full warp per row,
+empty / ragged rows, items never observed, and the C-ABI's error behaviour (never a crash)."""
+import importlib
+
+import numpy as np
+import pytest
+
+import ocffm
+import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b)))) if a.size else 0.0
+
+
+def pair(ds, prm, dtype, seed=3):
+    o = pyoracle.Oracle(ds, **prm)
+    p = ocffm.Problem(ds, dtype=dtype, **prm)
+    for (f1, f2, which), w in p.init_model(seed=seed).items():
+        o.set_block(f1, f2, which, w)
+    o.init_state()
+    p.init_state()
+    return o, p
+
+
+@pytest.mark.parametrize("k", [1, 5, 24, 64, 128])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_latent_sizes(k, dt):
+    """k is padded to 4, 8, 32, 64, 128 on the device (lane groups of 1..32 lanes per row)."""
+    synth = importlib.import_module("synth")
+    dtype, tol = (ocffm.F64, 1e-9) if dt == "f64" else (ocffm.F32, 2e-4)
+    ds = synth.generate("tiny", seed=5, test_rows=30, cold_rows=2)
+    prm = dict(k=k, lam=0.5, omega=0.0625, r=-1.0, self_side=True, freq=False)
+    o, p = pair(ds, prm, dtype)
+    fu = p.fu
+    for (f1, f2, which) in [(0, fu, "W"), (1, fu + 1, "H"), (0, 1, "H"), (fu, fu, "W")]:
+        G = o.grad(f1, f2, which)
+        assert rel_err(p.grad(f1, f2, which), G) <= tol
+        assert rel_err(p.hess_vec(f1, f2, which, -G), o.hess_vec(f1, f2, which, -G)) <= tol
+    o.one_epoch()
+    p.one_epoch()
+    if dt == "f64":
+        assert int(p.stats().cg_iters) == o.cg_iters_total()
+        assert abs(p.objective() - o.func()) <= 1e-9 * abs(o.func())
+        for f1, f2 in p.blocks():
+            assert rel_err(p.get_block(f1, f2, "W"), o.get_block(f1, f2, "W")) <= 1e-7
+    ro, rp = o.validate(), p.validate()
+    assert abs(rp["ploss"] - ro["ploss"]) <= 50 * tol * abs(ro["ploss"])
+    if dt == "f64":
+        assert np.array_equal(rp["topk"], ro["topk"])
+        assert np.allclose(rp["ndcg"], ro["ndcg"], rtol=1e-9) and np.allclose(rp["prec"], ro["prec"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_empty_and_ragged_rows(dt):
+    """Most users without any label, most items never observed (U->n < V->m), a few long rows."""
+    synth = importlib.import_module("synth")
+    dtype, tol = (ocffm.F64, 1e-9) if dt == "f64" else (ocffm.F32, 2e-4)
+    ds = synth.generate("C1", seed=6, scale=0.05, test_rows=40, cold_rows=3, pos_override=0.4)
+    lens = np.diff(ds.train.rowptr.astype(np.int64))
+    assert (lens == 0).sum() > ds.m // 2 and ds.train.n_items <= ds.n
+    prm = dict(k=8, lam=1.0, omega=0.03125, r=-1.0, self_side=True, freq=False)
+    o, p = pair(ds, prm, dtype)
+    for v in ("a", "b", "sa", "sb", "ytilde_csr", "ytilde_csc"):
+        assert rel_err(p.vec(v), o.vec(v)) <= tol, v
+    o.one_epoch()
+    p.one_epoch()
+    for v in ("a", "b", "ytilde_csr"):
+        assert rel_err(p.vec(v), o.vec(v)) <= (1e-7 if dt == "f64" else 5e-2), v
+    ro, rp = o.validate(), p.validate()
+    if dt == "f64":
+        assert np.array_equal(rp["topk"], ro["topk"])
+        # fewer than 80 ranked items -> the tail of every list is padding, like the early `break`
+        if ds.train.n_items < 80:
+            assert np.all(rp["topk"][:, ds.train.n_items:] == 0xFFFFFFFF)
+
+
+def test_error_behaviour_of_the_abi():
+    synth = importlib.import_module("synth")
+    ds = synth.generate("tiny", seed=5, test_rows=10)
+    prm = dict(k=4, lam=0.5, omega=0.0625, r=-1.0)
+    p = ocffm.Problem(ds, **prm)
+    with pytest.raises(ocffm.OcffmError):      # solver before the model / state exist
+        p.one_epoch()
+    with pytest.raises(ocffm.OcffmError):
+        p.init_state()                          # blocks never set
+    p.init_model(seed=1)
+    with pytest.raises(ocffm.OcffmError):
+        p.grad(0, p.fu, "W")                    # init_state not called yet
+    p.init_state()
+    with pytest.raises(ocffm.OcffmError):
+        p.grad(1, 0, "W")                       # f1 > f2
+    with pytest.raises(AssertionError):
+        p.set_block(0, p.fu, "W", np.zeros((3, 4)))   # wrong shape is caught before the ABI
+    # a label beyond the item file: rejected (the reference would leave its two Y copies inconsistent)
+    bad = synth.generate("tiny", seed=5)
+    bad.train.idx = bad.train.idx.copy()
+    bad.train.idx[0] = bad.n + 3
+    with pytest.raises(ocffm.OcffmError):
+        ocffm.Problem(bad, **prm)
+    # --ns: same-side blocks do not exist
+    q = ocffm.Problem(ds, self_side=False, **prm)
+    with pytest.raises(ocffm.OcffmError):
+        q.set_block(0, 0, "W", np.zeros((q.block_rows(0, 0, "W"), 4)))
