@@ -279,6 +279,8 @@ def main():
                     avg_launch_ms=(st.hv_ms / st.hv_launches) if st.hv_launches else None,
                     share_of_step=(st.hv_ms / ms) if ms > 0 else None,
                     algo_bytes_per_launch=(st.hv_algo_bytes / st.hv_launches) if st.hv_launches else None,
+                    gather_gbs=(st.hv_launches * ds.train.idx.size * k * (4 if args.dtype == "f32" else 8) / 1e9)
+                    / (st.hv_ms / 1e3) if st.hv_ms > 0 else None,
                     whole_epoch_gbs=(st.algo_bytes / 1e9) / sec)
 
     # ---- evaluation (validate, ffm.cpp:925-1016) --------------------------------------------
