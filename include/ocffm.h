@@ -111,6 +111,11 @@ OCFFM_API int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int whic
  * block, cache_sasb, calc_side, init_y_tilde. */
 OCFFM_API int ocffm_init_state(ocffm_ctx *ctx);
 
+/* (lambda, omega, r) sweeps over one uploaded data set (script/grid.sh:186-240 runs a 12 x 3 grid of
+ * solves on the same files): change the hyper-parameters of a live context; data, CSC, work lists
+ * and hot-feature tables stay resident.  Set the model blocks and call ocffm_init_state again. */
+OCFFM_API int ocffm_set_hyper(ocffm_ctx *ctx, double lambda, double omega, double r);
+
 /* ---- solver (ffm.cpp:815-870) ---- */
 OCFFM_API int ocffm_solve_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2); /* solve_side / solve_cross */
 OCFFM_API int ocffm_one_epoch(ocffm_ctx *ctx);                             /* one_epoch */

@@ -132,6 +132,7 @@ struct CtxBase {
                                  const uint64_t *nnx) = 0;
     virtual void set_block(uint32_t f1, uint32_t f2, int which, const double *data, uint64_t rows) = 0;
     virtual void get_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) = 0;
+    virtual void set_hyper(double lambda, double omega, double r) = 0;
     virtual void init_state() = 0;
     virtual void solve_block(uint32_t f1, uint32_t f2) = 0;
     virtual void one_epoch() = 0;
@@ -568,6 +569,12 @@ struct Problem final : CtxBase {
         algo_bytes += uint64_t(Fx) * (m + n) * k * sizeof(T) + (m + n) * sizeof(T);
     }
 
+    void set_hyper(double lambda, double omega, double r) override {
+        prm.lambda = lambda;
+        prm.omega = omega;
+        prm.r = r;
+        state_ready = false;   // y-tilde and the caches depend on nothing but the model; rebuild anyway
+    }
     void init_state() override {
         OC_REQUIRE(YU.set && YV.set, "labels not set");
         for (auto &F : XU) OC_REQUIRE(F.set, "a user field is missing");
@@ -1334,6 +1341,9 @@ int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double 
         OC_REQUIRE(data, "null array");
         c.get_block(f1, f2, which, data, rows);
     });
+}
+int ocffm_set_hyper(ocffm_ctx *ctx, double lambda, double omega, double r) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.set_hyper(lambda, omega, r); });
 }
 int ocffm_init_state(ocffm_ctx *ctx) {
     return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.init_state(); });

@@ -77,6 +77,10 @@ public:
     void print_data_info();
     void split_fields();
     void transY(const std::vector<Node *> &YT);
+    // additions: read() parses line ranges in parallel (OpenMP threads); a parsed
+    // and split file can be cached in binary form and reloaded instead of re-parsing the text
+    void save_cache(const std::string &path) const;   // call after split_fields()
+    bool load_cache(const std::string &path);         // false: missing / stale / corrupt
 };
 
 class ImpProblem {

@@ -15,6 +15,9 @@
 #include <iostream>
 #include <random>
 #include <stdexcept>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 using namespace std;
 
@@ -65,7 +68,15 @@ void parse_labels(const char *b, const char *e, vector<ImpInt> &out) {
     while (p < e) {
         const char *q = p;
         while (q < e && *q != ',') ++q;
-        out.push_back(ImpInt(stoi(string(p, q))));   // throws invalid_argument("stoi") on junk
+        // fast path for plain digits; anything else goes through stoi for identical semantics
+        // (leading blanks / sign accepted, trailing junk ignored, invalid_argument("stoi") on junk)
+        bool plain = q > p && q - p <= 9;
+        ImpInt v = 0;
+        for (const char *d = p; plain && d < q; ++d) {
+            if (*d < '0' || *d > '9') plain = false;
+            else v = v * 10 + ImpInt(*d - '0');
+        }
+        out.push_back(plain ? v : ImpInt(stoi(string(p, q))));
         p = q + 1;
     }
 }
@@ -103,28 +114,39 @@ void check(int rc, const char *what) {
 // ---------------------------------------------------------------------------------------------
 // ImpData
 // ---------------------------------------------------------------------------------------------
-void ImpData::read(bool has_label, const ImpLong *ds) {
-    const string buf = slurp(file_name);
-    Cursor c{buf.data(), buf.data() + buf.size()};
+// One contiguous range of lines parsed by one thread (the reference's two-pass
+// istringstream reader is serial and dominates end-to-end time once an epoch takes milliseconds).
+namespace {
+struct ParsedChunk {
+    vector<ImpInt> labels;          // concatenated label lists of the chunk's lines
+    vector<ImpLong> label_end;      // per line: end offset into `labels`
+    vector<Node> nodes;             // kept features of the chunk's lines
+    vector<ImpLong> node_end;       // per line: end offset into `nodes`
+    ImpLong max_label1 = 0, max_fid1 = 0;
+    bool bad_label = false;
+};
+
+void parse_range(const char *b, const char *e, bool has_label, const ImpLong *ds, ParsedChunk &out) {
+    Cursor c{b, e};
     vector<ImpInt> labels;
-    m = 0;
-    M.clear(); N.clear(); nnx.clear(); nny.clear();
-    y_rowptr.assign(1, 0);
-    y_idx.clear();
-    vector<ImpLong> xptr(1, 0);
     while (c.p < c.end) {
         const char *eol = static_cast<const char *>(memchr(c.p, '\n', size_t(c.end - c.p)));
         const char *line_end = eol ? eol : c.end;
         Cursor ln{c.p, line_end};
         if (has_label) {
             ln.skip_blank();
-            const char *b = ln.p;
+            const char *lb = ln.p;
             while (ln.p < ln.end && *ln.p != ' ' && *ln.p != '\t' && *ln.p != '\r') ++ln.p;
             labels.clear();
-            parse_labels(b, ln.p, labels);
+            try {
+                parse_labels(lb, ln.p, labels);
+            } catch (const exception &) {
+                out.bad_label = true;      // re-thrown as invalid_argument("stoi") by the caller
+                return;
+            }
             for (ImpInt j : labels) {
-                n = max<ImpLong>(n, ImpLong(j) + 1);
-                y_idx.push_back(j);
+                out.max_label1 = max<ImpLong>(out.max_label1, ImpLong(j) + 1);
+                out.labels.push_back(j);
             }
         }
         ImpLong fid, idx;
@@ -133,18 +155,70 @@ void ImpData::read(bool has_label, const ImpLong *ds) {
             if (!parse_ulong(ln, fid) || !parse_sep(ln) || !parse_ulong(ln, idx) || !parse_sep(ln) ||
                 !parse_double(ln, val))
                 break;
-            f = max(f, fid + 1);
+            out.max_fid1 = max(out.max_fid1, fid + 1);
             if (ds != nullptr && ds[fid] <= idx) continue;   // out-of-vocabulary test feature
             Node nd;
             nd.fid = ImpInt(fid);
             nd.idx = idx;
             nd.val = val;
-            N.push_back(nd);
+            out.nodes.push_back(nd);
         }
-        xptr.push_back(N.size());
-        y_rowptr.push_back(y_idx.size());
-        ++m;
+        out.label_end.push_back(out.labels.size());
+        out.node_end.push_back(out.nodes.size());
         c.p = eol ? eol + 1 : c.end;
+    }
+}
+}  // namespace
+
+void ImpData::read(bool has_label, const ImpLong *ds) {
+    const string buf = slurp(file_name);
+    const char *base = buf.data(), *end = buf.data() + buf.size();
+    // cut the buffer at line boundaries, one range per thread
+    int nthreads = 1;
+#ifdef _OPENMP
+    const char *mc = getenv("OCFFM_READER_CHUNK");          // smallest range worth a thread (tests lower it)
+    const size_t min_chunk = mc ? size_t(max(1, atoi(mc))) : size_t(1 << 16);
+    nthreads = max(1, min(omp_get_max_threads(), int(buf.size() / min_chunk) + 1));
+#endif
+    vector<const char *> cut(nthreads + 1, end);
+    cut[0] = base;
+    for (int t = 1; t < nthreads; t++) {
+        const char *p = base + buf.size() * size_t(t) / size_t(nthreads);
+        if (p < cut[t - 1]) p = cut[t - 1];
+        const char *nl = p < end ? static_cast<const char *>(memchr(p, '\n', size_t(end - p))) : nullptr;
+        cut[t] = nl ? nl + 1 : end;
+    }
+    vector<ParsedChunk> chunks(nthreads);
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+    for (int t = 0; t < nthreads; t++) parse_range(cut[t], cut[t + 1], has_label, ds, chunks[t]);
+    for (const ParsedChunk &c : chunks)
+        if (c.bad_label) throw invalid_argument("stoi");
+
+    // stitch the ranges together in file order
+    m = 0;
+    ImpLong tot_lab = 0, tot_nodes = 0;
+    for (const ParsedChunk &c : chunks) {
+        m += c.node_end.size();
+        tot_lab += c.labels.size();
+        tot_nodes += c.nodes.size();
+        n = max(n, c.max_label1);
+        f = max(f, c.max_fid1);
+    }
+    M.clear();
+    N.resize(tot_nodes);
+    y_idx.resize(tot_lab);
+    y_rowptr.assign(m + 1, 0);
+    vector<ImpLong> xptr(m + 1, 0);
+    ImpLong row = 0, lab0 = 0, nod0 = 0;
+    for (const ParsedChunk &c : chunks) {
+        copy(c.labels.begin(), c.labels.end(), y_idx.begin() + lab0);
+        copy(c.nodes.begin(), c.nodes.end(), N.begin() + nod0);
+        for (size_t i = 0; i < c.node_end.size(); i++, row++) {
+            y_rowptr[row + 1] = lab0 + c.label_end[i];
+            xptr[row + 1] = nod0 + c.node_end[i];
+        }
+        lab0 += c.labels.size();
+        nod0 += c.nodes.size();
     }
     nnz_x = N.size();
     nnx.resize(m);
@@ -169,6 +243,70 @@ void ImpData::read(bool has_label, const ImpLong *ds) {
         for (ImpDouble v : popular) total += v;
         for (ImpDouble &v : popular) v /= total;
     }
+}
+
+// ---- binary cache of a parsed + split file --------------------------------------
+// Layout: magic "OCFFMBIN1", source size, then m n f nnz_x nnz_y, Ds, nnx, nny, per field
+// (rowptr, idx, val, freq), y_rowptr, y_idx, popular.  A cache is used only if the text file's
+// size matches what was recorded when it was written.
+namespace {
+template <typename T>
+void put_vec(ofstream &o, const vector<T> &v) {
+    const uint64_t n = v.size();
+    o.write(reinterpret_cast<const char *>(&n), sizeof n);
+    if (n) o.write(reinterpret_cast<const char *>(v.data()), streamsize(n * sizeof(T)));
+}
+template <typename T>
+bool get_vec(ifstream &i, vector<T> &v) {
+    uint64_t n = 0;
+    if (!i.read(reinterpret_cast<char *>(&n), sizeof n)) return false;
+    v.resize(n);
+    return n == 0 || bool(i.read(reinterpret_cast<char *>(v.data()), streamsize(n * sizeof(T))));
+}
+uint64_t file_size_of(const string &path) {
+    ifstream in(path, ios::binary | ios::ate);
+    return in ? uint64_t(in.tellg()) : 0;
+}
+}  // namespace
+
+void ImpData::save_cache(const string &path) const {
+    ofstream o(path, ios::binary | ios::trunc);
+    o.write("OCFFMBIN1", 9);
+    const uint64_t src = file_size_of(file_name);
+    o.write(reinterpret_cast<const char *>(&src), sizeof src);
+    const uint64_t hdr[5] = {m, n, f, nnz_x, nnz_y};
+    o.write(reinterpret_cast<const char *>(hdr), sizeof hdr);
+    put_vec(o, Ds); put_vec(o, nnx); put_vec(o, nny);
+    for (ImpLong fi = 0; fi < f; fi++) {
+        put_vec(o, Xf[fi].rowptr); put_vec(o, Xf[fi].idx); put_vec(o, Xf[fi].val); put_vec(o, freq[fi]);
+    }
+    put_vec(o, y_rowptr); put_vec(o, y_idx); put_vec(o, popular);
+}
+
+bool ImpData::load_cache(const string &path) {
+    ifstream i(path, ios::binary);
+    char magic[9];
+    if (!i || !i.read(magic, 9) || memcmp(magic, "OCFFMBIN1", 9) != 0) return false;
+    uint64_t src = 0, hdr[5];
+    if (!i.read(reinterpret_cast<char *>(&src), sizeof src) || src != file_size_of(file_name)) return false;
+    if (!i.read(reinterpret_cast<char *>(hdr), sizeof hdr)) return false;
+    m = hdr[0]; n = hdr[1]; f = hdr[2]; nnz_x = hdr[3]; nnz_y = hdr[4];
+    if (!get_vec(i, Ds) || !get_vec(i, nnx) || !get_vec(i, nny)) return false;
+    Xf.assign(f, FieldCSR());
+    freq.assign(f, vector<ImpLong>());
+    for (ImpLong fi = 0; fi < f; fi++)
+        if (!get_vec(i, Xf[fi].rowptr) || !get_vec(i, Xf[fi].idx) || !get_vec(i, Xf[fi].val) || !get_vec(i, freq[fi]))
+            return false;
+    if (!get_vec(i, y_rowptr) || !get_vec(i, y_idx) || !get_vec(i, popular)) return false;
+    // rebuild the Node view of the labels (Y is what transY() consumes)
+    M.assign(y_idx.size(), Node());
+    for (size_t t = 0; t < y_idx.size(); t++) M[t].idx = y_idx[t];
+    Y.resize(m + 1);
+    if (y_rowptr.size() == m + 1)
+        for (ImpLong r = 0; r <= m; r++) Y[r] = M.data() + y_rowptr[r];
+    X.clear();
+    N.clear();
+    return true;
 }
 
 void ImpData::split_fields() {

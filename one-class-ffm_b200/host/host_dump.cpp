@@ -51,14 +51,29 @@ int main(int argc, char **argv) {
     shared_ptr<ImpData> U = make_shared<ImpData>(argv[2]);
     shared_ptr<ImpData> V = make_shared<ImpData>(argv[1]);
     shared_ptr<ImpData> Ut = make_shared<ImpData>(strcmp(argv[3], "-") ? argv[3] : "");
+    // optional last argument "--via-cache <dir>": every file goes text -> cache -> fresh object
+    string cache_dir;
+    for (int i = 6; i + 1 < argc; i++)
+        if (!strcmp(argv[i], "--via-cache")) cache_dir = argv[i + 1];
+    auto roundtrip = [&](shared_ptr<ImpData> &d, const char *tag) {
+        if (cache_dir.empty()) return;
+        const string path = cache_dir + "/" + tag + ".bin";
+        d->save_cache(path);
+        shared_ptr<ImpData> fresh = make_shared<ImpData>(d->file_name);
+        if (!fresh->load_cache(path)) { fprintf(stderr, "cache reload failed for %s\n", tag); exit(3); }
+        d = fresh;
+    };
     U->read(true);
     U->split_fields();
+    roundtrip(U, "U");
     V->read(false);
-    V->transY(U->Y);
     V->split_fields();
+    roundtrip(V, "V");
+    V->transY(U->Y);
     if (!Ut->file_name.empty()) {
         Ut->read(true, U->Ds.data());
         Ut->split_fields();
+        roundtrip(Ut, "T");
     }
     g_out = fopen(argv[4], "wb");
     fputs("OCFD1\n", g_out);

@@ -15,6 +15,9 @@
 #include <stdexcept>
 
 #include "ffm.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 using namespace std;
 
@@ -23,7 +26,7 @@ namespace {
 struct Option {
     shared_ptr<Parameter> param = make_shared<Parameter>();
     string item_path, train_path, test_path, model_path, load_path, binary_path;
-    bool predict_only = false;
+    bool predict_only = false, cache = false;
 };
 
 bool has_digit(const char *s) {
@@ -50,7 +53,8 @@ const char *kUsage =
     "--device <n>: CUDA device ordinal\n"
     "--load <path>: start from a binary model (save_binary_model layout)\n"
     "--save-binary <path>: also write the binary model\n"
-    "--predict-only: evaluate the loaded model on the test set and exit\n";
+    "--predict-only: evaluate the loaded model on the test set and exit\n"
+    "--cache: keep / reuse <file>.ocffm.bin binary caches of the parsed text files\n";
 
 // value of a numeric flag; `miss` is thrown when the value is absent, `bad` when it has no digit
 const char *numeric_value(int argc, char **argv, int &i, const char *miss, const char *bad) {
@@ -82,6 +86,7 @@ Option parse_option(int argc, char **argv) {
         else if (a == "--freq") p.freq = true;
         else if (a == "--f64") p.dtype = OCFFM_F64;
         else if (a == "--predict-only") opt.predict_only = true;
+        else if (a == "--cache") opt.cache = true;
         else break;   // first non-flag token ends option parsing
     }
     if (i >= argc) throw invalid_argument("training data not specified");
@@ -99,15 +104,28 @@ int main(int argc, char *argv[]) {
         shared_ptr<ImpData> V = make_shared<ImpData>(opt.item_path);
         shared_ptr<ImpData> Ut = make_shared<ImpData>(opt.test_path);
 
-        U->read(true);
-        U->split_fields();
-        V->read(false);
-        V->transY(U->Y);
-        V->split_fields();
-        if (!Ut->file_name.empty()) {
-            Ut->read(true, U->Ds.data());
-            Ut->split_fields();
+#ifdef _OPENMP
+        omp_set_num_threads(int(opt.param->nr_threads));   // -c: host threads (reader), train.cpp:174
+#endif
+        // parse (in parallel) or reload the binary cache of an earlier parse
+        auto load = [&](shared_ptr<ImpData> &d, bool has_label, const ImpLong *ds, const char *tag) {
+            const string cpath = d->file_name + (ds ? string(".") + tag : string("")) + ".ocffm.bin";
+            if (opt.cache && d->load_cache(cpath)) return;
+            d->read(has_label, ds);
+            d->split_fields();
+            if (opt.cache) d->save_cache(cpath);
+        };
+        load(U, true, nullptr, "tr");
+        {   // the item file's labels come from transY, which must run before its fields are cached
+            const string cpath = V->file_name + ".ocffm.bin";
+            if (!(opt.cache && V->load_cache(cpath))) {
+                V->read(false);
+                V->split_fields();
+                if (opt.cache) V->save_cache(cpath);
+            }
+            V->transY(U->Y);
         }
+        if (!Ut->file_name.empty()) load(Ut, true, U->Ds.data(), "te");
 
         ImpProblem prob(U, Ut, V, opt.param);
         if (!opt.load_path.empty()) prob.load_binary_model(opt.load_path);

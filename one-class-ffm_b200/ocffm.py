@@ -43,7 +43,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "ocffm_abi_version", "ocffm_last_error", "ocffm_device_count", "ocffm_create", "ocffm_destroy",
     "ocffm_comm_unique_id", "ocffm_shard_range", "ocffm_comm_init", "ocffm_set_field", "ocffm_set_labels",
-    "ocffm_set_test_labels", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
+    "ocffm_set_test_labels", "ocffm_set_hyper", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
     "ocffm_solve_block", "ocffm_one_epoch", "ocffm_grad", "ocffm_hess_vec", "ocffm_cg",
     "ocffm_objective", "ocffm_validate", "ocffm_get_vec", "ocffm_get_embed", "ocffm_get_csc",
     "ocffm_get_stats", "ocffm_reset_stats", "ocffm_synchronize", "ocffm_stream",
@@ -77,6 +77,7 @@ def lib():
         L.ocffm_set_block.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
         L.ocffm_get_block.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
         L.ocffm_init_state.argtypes = [vp]
+        L.ocffm_set_hyper.argtypes = [vp, C.c_double, C.c_double, C.c_double]
         L.ocffm_solve_block.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.ocffm_one_epoch.argtypes = [vp]
         L.ocffm_grad.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
@@ -241,6 +242,10 @@ class Problem:
 
     def init_state(self):
         self._ck(self.L.ocffm_init_state(self.h))
+
+    def set_hyper(self, lam: float, omega: float, r: float = -1.0):
+        """New (lambda, omega, r) on the resident data; set blocks + init_state() afterwards."""
+        self._ck(self.L.ocffm_set_hyper(self.h, lam, omega, r))
 
     def vec(self, name: str) -> np.ndarray:
         cnt = C.c_uint64(0)

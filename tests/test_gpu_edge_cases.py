@@ -105,3 +105,26 @@ def test_error_behaviour_of_the_abi():
     q = ocffm.Problem(ds, self_side=False, **prm)
     with pytest.raises(ocffm.OcffmError):
         q.set_block(0, 0, "W", np.zeros((q.block_rows(0, 0, "W"), 4)))
+
+
+def test_hyper_parameter_sweep_reuses_resident_data():
+    """grid.sh-style sweep: one upload, several (lambda, omega) solves == fresh contexts (fp64)."""
+    synth = importlib.import_module("synth")
+    ds = synth.generate("C1", seed=9, scale=0.05, test_rows=40)
+    base = dict(k=8, r=-1.0, self_side=True, freq=False)
+    p = ocffm.Problem(ds, dtype=ocffm.F64, lam=1.0, omega=0.5, **base)
+    model = p.init_model(seed=4)
+    for lam, omega in [(4.0, 2.0 ** -7), (16.0, 2.0 ** -3), (1.0, 1.0)]:
+        p.set_hyper(lam, omega, -1.0)
+        for key, w in model.items():
+            p.set_block(*key, w)
+        p.init_state()
+        p.one_epoch()
+        fresh = ocffm.Problem(ds, dtype=ocffm.F64, lam=lam, omega=omega, **base)
+        for key, w in model.items():
+            fresh.set_block(*key, w)
+        fresh.init_state()
+        fresh.one_epoch()
+        assert abs(p.objective() - fresh.objective()) <= 1e-11 * abs(fresh.objective())
+        assert np.allclose(p.validate()["ndcg"], fresh.validate()["ndcg"], rtol=1e-9)
+        fresh.close()

@@ -23,16 +23,23 @@ def built():
 
 
 @pytest.mark.parametrize("case", ["tiny", "tiny_ns", "tiny_freq", "small"])
-def test_reader_split_fields_transY_and_init_match_reference(case):
+@pytest.mark.parametrize("mode", ["serial", "parallel", "via_cache"])
+def test_reader_split_fields_transY_and_init_match_reference(case, mode):
+    """serial: one thread; parallel: 5 OpenMP threads over ~64-byte line ranges; via_cache: every
+    parsed file goes through save_cache/load_cache before it is used."""
     d = load_golden(case)
     prm, _ = params_of(d)
     base = os.path.join(GOLDEN, case, case)
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "h.ocfd")
         cmd = [HOST_DUMP, base + ".item", base + ".tr", base + ".te", out, str(prm["k"])]
-        if not prm["self_side"]:
-            cmd.append("--ns")
-        subprocess.check_call(cmd)
+        cmd.append("--ns" if not prm["self_side"] else "--side")
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        if mode == "parallel":
+            env.update(OMP_NUM_THREADS="5", OCFFM_READER_CHUNK="64")
+        if mode == "via_cache":
+            cmd += ["--via-cache", tmp]
+        subprocess.check_call(cmd, env=env)
         h = pyoracle.load_ocfd(out)
     assert len(h) > 30
     for name, got in h.items():
