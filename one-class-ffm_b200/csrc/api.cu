@@ -167,6 +167,7 @@ struct Problem final : CtxBase {
     cudaStream_t st = nullptr;
     Comm comm;
     uint32_t chunk = 64;
+    bool diag_fast = true;      // OCFFM_DIAG_FAST=0 disables the fused same-side CG pass
     uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
     bool profile = false;
 
@@ -177,6 +178,7 @@ struct Problem final : CtxBase {
         DevBuf<T> val, freq, shadow;
         DevBuf<int16_t> hot_slot;
         uint32_t n_hot = 0;
+        bool diagonal = false;   // one feature per row, features form a permutation of 0..D-1
         uint32_t row0 = 0, row1 = 0;
         CsrView<T> view() const {
             return {rowptr.p, idx.p, val.p, row0, row1, n_hot ? hot_slot.p : nullptr, shadow.p};
@@ -269,6 +271,7 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
         if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
+        if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
         a.zero(st); b.zero(st); sa.zero(st); sb.zero(st);
@@ -340,6 +343,12 @@ struct Problem final : CtxBase {
             OC_REQUIRE(idx[t] < D, "feature index >= D");
             v[t] = T(val[t]);
             fr[idx[t]] += T(1);   // freq, ffm.cpp:235-241
+        }
+        F.diagonal = false;
+        if (nnz == rows && D == rows && rows > 0) {
+            bool ok = true;
+            for (uint64_t i = 0; i < rows && ok; ++i) ok = rowptr[i] == i && fr[idx[i]] == T(1);
+            F.diagonal = ok;
         }
         F.rowptr.upload(rp, st);
         F.idx.upload(idx, nnz, st);
@@ -786,9 +795,15 @@ struct Problem final : CtxBase {
     // speculative iteration past the stop is a no-op and the GPU never idles on the host.
     void enqueue_cg_iter(const Half &h, int it) {
         const uint64_t len = h.D * kp;
-        cg_dir<T>(V.p, R.p, Hv.p, len, it, sc, st);
-        hess_scatter(h, Gate{sc, it});
-        cg_reg_dot<T>(Hv.p, V.p, h.freq, T(prm.lambda), h.D, kp, it, sc, 1, st);
+        if (h.side && h.X->diagonal && !comm.active() && diag_fast) {
+            // row-local Hessian: direction update, Hv, regulariser and V.Hv in one pass
+            side_diag_iter<T>(h.Yown->view(), h.X->view(), h.Q1, V.p, R.p, Hv.p, h.freq, T(prm.lambda),
+                              T(prm.omega), T(h.n1), kp, it, sc, st);
+        } else {
+            cg_dir<T>(V.p, R.p, Hv.p, len, it, sc, st);
+            hess_scatter(h, Gate{sc, it});
+            cg_reg_dot<T>(Hv.p, V.p, h.freq, T(prm.lambda), h.D, kp, it, sc, 1, st);
+        }
         cg_step<T>(S.p, R.p, V.p, Hv.p, len, it, sc, st);
         OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaEventRecord(cg_ev[it], st));

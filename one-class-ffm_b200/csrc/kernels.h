@@ -94,6 +94,14 @@ void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1
                const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
                int kp, Gate gate, cudaStream_t s);
 
+// Same-side CG iteration on a DIAGONAL field (every row has exactly one feature and the features
+// form a permutation, e.g. a user-id / item-id field): hs_side (ffm.cpp:603-624) is then local to
+// a row, so cg_dir + side_rows<1> + cg_reg_dot collapse into one pass without atomics:
+//   v = (it ? R_f + beta V_f : V_f);  Hv_f = lambda_f v + q_i x d_i (q_i . x v);  vHv += v . Hv_f
+template <typename T>
+void side_diag_iter(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, const T *R, T *Hv,
+                    const T *freq, T lambda, T w, T n1, int kp, int it, SolveScalars *sc, cudaStream_t s);
+
 // y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
 template <typename T>
 void sddmm_add(const OmegaView<T> &Y, const T *Uown, uint32_t ldu, const T *Vo, uint32_t ldv,

@@ -294,6 +294,62 @@ k_side_rows(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, const T *__r
         red4(scatter_row(X, Out, X.idx[t], kp) + lg * 4, scale4(q, X.val[t] * z));
 }
 
+// block-wide fp64 sum + deterministic last-block combine (same scheme as dense.cu's finish_sum)
+__device__ __forceinline__ void finish_sum_rows(double local, SolveScalars *sc, double *out) {
+    __shared__ bool is_last;
+    local = block_sum(local);
+    if (threadIdx.x == 0) {
+        sc->partials[blockIdx.x] = local;
+        __threadfence();
+        const unsigned t = atomicInc(&sc->counter[0], gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double sum = 0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+            sum += reinterpret_cast<volatile double *>(sc->partials)[i];
+        sum = block_sum(sum);
+        if (threadIdx.x == 0) *out = sum;
+    }
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads)
+k_side_diag_iter(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__restrict__ V,
+                 const T *__restrict__ R, T *__restrict__ Hv, const T *__restrict__ freq, T lambda, T w, T n1,
+                 int it, SolveScalars *sc) {
+    constexpr uint32_t kp = 4 * G;
+    if (!gate_open(Gate{sc, it})) return;
+    const T beta = it > 0 ? T(sc->r2[it] / sc->r2[it - 1]) : T(0);
+    const uint32_t rows = X.row1 - X.row0;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    double local = 0;
+    const uint64_t groups_total = uint64_t(gridDim.x) * blockDim.x / G;
+    for (uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G; g < rows; g += groups_total) {
+        const uint32_t row = X.row0 + uint32_t(g);
+        const uint32_t f = X.idx[row];          // rowptr[row] == row on a diagonal field
+        const T x = X.val[row];
+        const size_t off = size_t(f) * kp + lg * 4;
+        V4<T> v = ld4(V + off);
+        if (it > 0) {
+            const V4<T> r = ld4(R + off);
+            v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
+            st4(V + off, v);
+        }
+        const V4<T> q = ldg4(Q1 + size_t(row) * kp + lg * 4);
+        const T cnt = T(Y.rowptr[row + 1] - Y.rowptr[row]);
+        const T z = gsum<G>(dot4(q, v), mask) * x * ((T(1) - w) * cnt + w * n1) * x;
+        const T c = freq ? lambda * freq[f] : lambda;
+        const V4<T> h = {c * v.x + q.x * z, c * v.y + q.y * z, c * v.z + q.z * z, c * v.w + q.w * z};
+        st4(Hv + off, h);
+        local += double(v.x) * h.x + double(v.y) * h.y + double(v.z) * h.z + double(v.w) * h.w;
+    }
+    finish_sum_rows(local, sc, &sc->vHv[it]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_ytilde_base(OmegaView<T> Y, const T *__restrict__ a_own, const T *__restrict__ b_oth) {
@@ -437,6 +493,17 @@ void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1
 }
 
 template <typename T>
+void side_diag_iter(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, const T *R, T *Hv,
+                    const T *freq, T lambda, T w, T n1, int kp, int it, SolveScalars *sc, cudaStream_t s) {
+    const uint64_t rows = X.row1 - X.row0;
+    if (!rows) return;
+    OC_DISPATCH_G(kp, {
+        const unsigned blocks = std::min<unsigned>(blocks_for(rows, G), unsigned(kSMs) * 8u);
+        OC_LAUNCH((k_side_diag_iter<T, G>), blocks, kThreads, 0, s, Y, X, Q1, V, R, Hv, freq, lambda, w, n1, it, sc);
+    });
+}
+
+template <typename T>
 void sddmm_add(const OmegaView<T> &Y, const T *Uown, uint32_t ldu, const T *Vo, uint32_t ldv,
                int kp, cudaStream_t s) {
     if (!Y.n_items) return;
@@ -494,6 +561,8 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
     template void sddmm_add<T>(const OmegaView<T> &, const T *, uint32_t, const T *, uint32_t, int, \
                                cudaStream_t);                                                      \
     template void ytilde_base<T>(const OmegaView<T> &, const T *, const T *, cudaStream_t);        \
+    template void side_diag_iter<T>(const OmegaView<T> &, const CsrView<T> &, const T *, T *, const T *, T *, \
+                                    const T *, T, T, T, int, int, SolveScalars *, cudaStream_t);   \
     template void ytilde_add_gap<T>(const OmegaView<T> &, const T *, int, cudaStream_t);           \
     template void rowwise_dot<T>(const T *, const T *, uint32_t, int, T *, int, cudaStream_t);     \
     template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);
