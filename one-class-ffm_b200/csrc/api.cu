@@ -168,6 +168,7 @@ struct Problem final : CtxBase {
     Comm comm;
     uint32_t chunk = 64;
     bool diag_fast = true;      // OCFFM_DIAG_FAST=0 disables the fused same-side CG pass
+    bool slice_cg = true;       // OCFFM_SLICE_CG=0: always replicate CG vectors across ranks
     uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
     bool profile = false;
 
@@ -179,6 +180,7 @@ struct Problem final : CtxBase {
         DevBuf<int16_t> hot_slot;
         uint32_t n_hot = 0;
         bool diagonal = false;   // one feature per row, features form a permutation of 0..D-1
+        bool identity = false;   // diagonal with idx[i] == i: a rank's rows touch only its own feature slice
         uint32_t row0 = 0, row1 = 0;
         CsrView<T> view() const {
             return {rowptr.p, idx.p, val.p, row0, row1, n_hot ? hot_slot.p : nullptr, shadow.p};
@@ -272,6 +274,7 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_SLICE_CG")) slice_cg = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
         a.zero(st); b.zero(st); sa.zero(st); sb.zero(st);
@@ -349,6 +352,9 @@ struct Problem final : CtxBase {
             bool ok = true;
             for (uint64_t i = 0; i < rows && ok; ++i) ok = rowptr[i] == i && fr[idx[i]] == T(1);
             F.diagonal = ok;
+            bool id = ok;
+            for (uint64_t i = 0; i < rows && id; ++i) id = idx[i] == i;
+            F.identity = id;
         }
         F.rowptr.upload(rp, st);
         F.idx.upload(idx, nnz, st);
@@ -637,6 +643,11 @@ struct Problem final : CtxBase {
         uint32_t ldq, ldp;
         T *a1, *b1, *sa1;
         const T *freq;
+        // Multi-rank, identity field: features [s0, s1) are touched by this rank's rows only, so
+        // G / Hv need no all-reduce and all CG vector work runs on the slice (scalars are reduced)
+        bool sliced;
+        uint64_t s0, s1;
+        size_t soff() const { return size_t(s0); }
     };
     Half half_of(uint32_t f1, uint32_t f2, int which) {
         OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
@@ -671,6 +682,9 @@ struct Problem final : CtxBase {
         }
         const uint64_t len = h.D * kp;
         G.ensure(len); S.ensure(len); R.ensure(len); V.ensure(len); VQ.ensure(len); Hv.ensure(len);
+        h.sliced = comm.active() && h.X->identity && slice_cg;
+        h.s0 = h.sliced ? h.X->row0 : 0;
+        h.s1 = h.sliced ? h.X->row1 : h.D;
         return h;
     }
 
@@ -720,7 +734,7 @@ struct Problem final : CtxBase {
                           uint64_t(Fx) * h.m1 * k * s + h.m1 * s + nnzX * (4 + s) + 2 * h.D * k * s;
         }
         if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, G.p, kp, st);
-        comm.allreduce(G.p, h.D * kp, st);
+        if (!h.sliced) comm.allreduce(G.p, h.D * kp, st);
         nnz_trav += nnzY + nnzX;
     }
 
@@ -749,7 +763,7 @@ struct Problem final : CtxBase {
             side_rows<T>(1, h.Yown->view(), h.X->view(), h.Q1, nullptr, nullptr, nullptr, nullptr, V.p,
                          T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, gate, st);
         } else {
-            rowgemm<T>(V.p, kp, kp, qtq_of(h), VQ.p, h.D, kp, gate, st);
+            rowgemm<T>(V.p + h.soff() * kp, kp, kp, qtq_of(h), VQ.p + h.soff() * kp, h.s1 - h.s0, kp, gate, st);
             size_t ev = 0;
             if (profile) {
                 if (hv_events_used >= 4096) { sync(); drain_hv_events(); }
@@ -761,7 +775,7 @@ struct Problem final : CtxBase {
             if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
         }
         if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, Hv.p, kp, st);
-        comm.allreduce(Hv.p, h.D * kp, st);
+        if (!h.sliced) comm.allreduce(Hv.p, h.D * kp, st);
     }
     void account_hess(const Half &h, uint64_t iters) {
         const size_t s = sizeof(T);
@@ -794,23 +808,31 @@ struct Problem final : CtxBase {
     // side gate that re-evaluates the reference's stop test (g2 * 0.09 < r2, ffm.cpp:780), so a
     // speculative iteration past the stop is a no-op and the GPU never idles on the host.
     void enqueue_cg_iter(const Half &h, int it) {
-        const uint64_t len = h.D * kp;
-        if (h.side && h.X->diagonal && !comm.active() && diag_fast) {
+        const size_t o = h.soff() * kp;
+        const uint64_t Ds = h.s1 - h.s0, len = Ds * kp;
+        const T *fq = h.freq ? h.freq + h.soff() : nullptr;
+        if (h.side && h.X->diagonal && diag_fast && (!comm.active() || h.sliced)) {
             // row-local Hessian: direction update, Hv, regulariser and V.Hv in one pass
             side_diag_iter<T>(h.Yown->view(), h.X->view(), h.Q1, V.p, R.p, Hv.p, h.freq, T(prm.lambda),
                               T(prm.omega), T(h.n1), kp, it, sc, st);
         } else {
-            cg_dir<T>(V.p, R.p, Hv.p, len, it, sc, st);
+            cg_dir<T>(V.p + o, R.p + o, Hv.p + o, len, it, sc, st);
             hess_scatter(h, Gate{sc, it});
-            cg_reg_dot<T>(Hv.p, V.p, h.freq, T(prm.lambda), h.D, kp, it, sc, 1, st);
+            cg_reg_dot<T>(Hv.p + o, V.p + o, fq, T(prm.lambda), Ds, kp, it, sc, 1, st);
         }
-        cg_step<T>(S.p, R.p, V.p, Hv.p, len, it, sc, st);
+        if (h.sliced) comm.allreduce(&sc->vHv[it], 1, st);          // slice partial -> global V.Hv
+        cg_step<T>(S.p + o, R.p + o, V.p + o, Hv.p + o, len, it, sc, st);
+        if (h.sliced) comm.allreduce(&sc->r2[it + 1], 1, st);
         OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaEventRecord(cg_ev[it], st));
     }
     int run_cg(const Half &h, bool add_reg) {
+        const size_t o = h.soff() * kp;
+        const T *fq = h.freq ? h.freq + h.soff() : nullptr;
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
-        cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, st);
+        cg_init<T>(G.p + o, h.W1 + o, fq, add_reg ? T(prm.lambda) : T(0), R.p + o, V.p + o, S.p + o, h.s1 - h.s0,
+                   kp, sc, st);
+        if (h.sliced) comm.allreduce(&sc->r2[0], 1, st);
         const double g2 = read_scalar(&sc->r2[0]);
         const int max_cg = 20;
         const double eps = 9e-2;
@@ -835,7 +857,12 @@ struct Problem final : CtxBase {
     void apply_update(const Half &h) {
         const size_t s = sizeof(T);
         const uint64_t len = h.D * kp, nnzY = h.Yown->nnz, nnzX = h.X->nnz;
-        axpy<T>(h.W1, S.p, T(1), len, st);
+        if (h.sliced) {
+            axpy<T>(h.W1 + h.soff() * kp, S.p + h.soff() * kp, T(1), (h.s1 - h.s0) * kp, st);
+            comm.allgather_rows(h.W1, h.D, kp, st);   // once per half solve: replicas of W stay whole
+        } else {
+            axpy<T>(h.W1, S.p, T(1), len, st);
+        }
         const T *q_side = h.side ? h.Q1 : nullptr;
         if (!comm.active()) {
             spmm_update<T>(h.X->view_all(), S.p, XS.p, h.P1, h.ldp, q_side, gap.p, h.a1, kp, st);
@@ -948,6 +975,7 @@ struct Problem final : CtxBase {
         Half h = half_of(f1, f2, which);
         OC_REQUIRE(rows == h.D, "rows must equal Ds of the updated field");
         grad_scatter(h);
+        if (h.sliced) comm.allgather_rows(G.p, h.D, kp, st);
         add_reg_into(G.p, h.W1, h);
         download_unpadded(G.p, kp, Gout, h.D);
     }
@@ -959,6 +987,7 @@ struct Problem final : CtxBase {
         if (!h.side) prepare_cross(h);
         OC_CUDA(cudaMemsetAsync(Hv.p, 0, h.D * kp * sizeof(T), st));
         hess_scatter(h, kNoGate);
+        if (h.sliced) comm.allgather_rows(Hv.p, h.D, kp, st);
         add_reg_into(Hv.p, V.p, h);
         download_unpadded(Hv.p, kp, Hout, h.D);
     }
@@ -970,6 +999,7 @@ struct Problem final : CtxBase {
         if (!h.side) prepare_cross(h);
         const uint64_t before = cg_iters;
         const int it = run_cg(h, false);
+        if (h.sliced) comm.allgather_rows(S.p, h.D, kp, st);
         cg_iters = before;
         if (iters) *iters = it;
         download_unpadded(S.p, kp, Sout, h.D);
