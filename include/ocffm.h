@@ -152,9 +152,9 @@ typedef struct ocffm_stats {
     uint64_t cg_iters;          /* CG iterations since reset */
     uint64_t nnz_traversed;     /* SURVEY.md 8(d) N_trav since reset */
     uint64_t algo_bytes;        /* SURVEY.md 8(d) algorithmic bytes since reset */
-    /* phase times since reset, only with OCFFM_PROFILE=2: same-side halves grad / CG / update,
-     * then cross halves grad / CG / update */
-    double ms_grad, ms_hess, ms_cgvec, ms_update, ms_gram, ms_eval;
+    /* phase times (ms) since reset, only with OCFFM_PROFILE=2: gradient / CG / update of the
+     * same-side half solves, then of the cross half solves */
+    double ms_side_grad, ms_side_cg, ms_side_update, ms_cross_grad, ms_cross_cg, ms_cross_update;
     uint64_t hv_launches;       /* launches of the dominant kernel (hv_cross rows) */
     uint64_t hv_algo_bytes;     /* its algorithmic bytes since reset */
     double hv_ms;               /* its device time since reset (CUDA events, OCFFM_PROFILE=1) */

@@ -1197,8 +1197,8 @@ struct Problem final : CtxBase {
         out->hv_algo_bytes = hv_algo_bytes;
         out->hv_ms = hv_ms;
         // side: grad / cg / update ; cross: grad / cg / update  (OCFFM_PROFILE >= 2)
-        out->ms_grad = ms[0]; out->ms_hess = ms[1]; out->ms_cgvec = ms[2];
-        out->ms_update = ms[3]; out->ms_gram = ms[4]; out->ms_eval = ms[5];
+        out->ms_side_grad = ms[0]; out->ms_side_cg = ms[1]; out->ms_side_update = ms[2];
+        out->ms_cross_grad = ms[3]; out->ms_cross_cg = ms[4]; out->ms_cross_update = ms[5];
     }
     void reset_stats() override {
         sync();

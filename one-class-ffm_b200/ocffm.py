@@ -34,9 +34,9 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("cg_iters", C.c_uint64), ("nnz_traversed", C.c_uint64),
-                ("algo_bytes", C.c_uint64), ("ms_grad", C.c_double), ("ms_hess", C.c_double),
-                ("ms_cgvec", C.c_double), ("ms_update", C.c_double), ("ms_gram", C.c_double),
-                ("ms_eval", C.c_double), ("hv_launches", C.c_uint64), ("hv_algo_bytes", C.c_uint64),
+                ("algo_bytes", C.c_uint64), ("ms_side_grad", C.c_double), ("ms_side_cg", C.c_double),
+                ("ms_side_update", C.c_double), ("ms_cross_grad", C.c_double), ("ms_cross_cg", C.c_double),
+                ("ms_cross_update", C.c_double), ("hv_launches", C.c_uint64), ("hv_algo_bytes", C.c_uint64),
                 ("hv_ms", C.c_double)]
 
 

@@ -12,6 +12,6 @@ for _ in range(5): p.one_epoch()
 p.synchronize(); wall=(time.perf_counter()-t)/5*1e3
 s=p.stats()
 print("wall ms/epoch",wall,"cg",s.cg_iters/5,"launches",s.kernel_launches/5)
-print("side  grad %.2f cg %.2f upd %.2f"%(s.ms_grad/5,s.ms_hess/5,s.ms_cgvec/5))
-print("cross grad %.2f cg %.2f upd %.2f"%(s.ms_update/5,s.ms_gram/5,s.ms_eval/5))
+print("side  grad %.2f cg %.2f upd %.2f"%(s.ms_side_grad/5,s.ms_side_cg/5,s.ms_side_update/5))
+print("cross grad %.2f cg %.2f upd %.2f"%(s.ms_cross_grad/5,s.ms_cross_cg/5,s.ms_cross_update/5))
 print("hv ms/epoch",s.hv_ms/5,"launches",s.hv_launches/5)
