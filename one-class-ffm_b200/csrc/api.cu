@@ -234,7 +234,7 @@ struct Problem final : CtxBase {
     double *h_stage = nullptr; // pinned staging for model blocks crossing the ABI as fp64
     size_t h_stage_n = 0;
     DevBuf<double> d_stage;
-    cudaEvent_t cg_ev[24];
+    cudaEvent_t cg_ev[24], g2_ev;
 
     // stats
     uint64_t launches = 0, cg_iters = 0, nnz_trav = 0, algo_bytes = 0, hv_launches = 0,
@@ -257,6 +257,7 @@ struct Problem final : CtxBase {
         OC_CUDA(cudaMalloc(&sc, sizeof(SolveScalars)));
         OC_CUDA(cudaMallocHost(&h_scal, 64 * sizeof(double)));
         for (auto &e : cg_ev) OC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        OC_CUDA(cudaEventCreateWithFlags(&g2_ev, cudaEventDisableTiming));
         XU.resize(fu);
         XV.resize(fv);
         XT.resize(fu);
@@ -290,6 +291,7 @@ struct Problem final : CtxBase {
         cudaSetDevice(device);
         for (auto &e : hv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto &e : cg_ev) cudaEventDestroy(e);
+        cudaEventDestroy(g2_ev);
         if (sc) cudaFree(sc);
         if (h_scal) cudaFreeHost(h_scal);
         if (h_stage) cudaFreeHost(h_stage);
@@ -796,12 +798,6 @@ struct Problem final : CtxBase {
         algo_bytes += iters * 7 * h.D * k * s;
     }
 
-    double read_scalar(const double *dev) {
-        OC_CUDA(cudaMemcpyAsync(h_scal, dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-        sync();
-        return h_scal[0];
-    }
-
     // cg, ffm.cpp:744-813.  G holds the gradient WITHOUT lambda W when add_reg is set (solver
     // path, the regulariser is fused into cg_init), or the full gradient otherwise.
     // Iteration it+1 is enqueued before r2[it+1] has been read back; its kernels carry a device
@@ -833,12 +829,18 @@ struct Problem final : CtxBase {
         cg_init<T>(G.p + o, h.W1 + o, fq, add_reg ? T(prm.lambda) : T(0), R.p + o, V.p + o, S.p + o, h.s1 - h.s0,
                    kp, sc, st);
         if (h.sliced) comm.allreduce(&sc->r2[0], 1, st);
-        const double g2 = read_scalar(&sc->r2[0]);
+        // No hard stream sync in here: g2 is fetched asynchronously while iteration 0 (which the
+        // device gate closes by itself when g2 == 0) is already enqueued, and after the loop the
+        // stream order alone protects S / R / V -- the GPU never waits for the host.
+        OC_CUDA(cudaMemcpyAsync(h_scal, &sc->r2[0], sizeof(double), cudaMemcpyDeviceToHost, st));
+        OC_CUDA(cudaEventRecord(g2_ev, st));
         const int max_cg = 20;
         const double eps = 9e-2;
         int it = 0;
+        enqueue_cg_iter(h, 0);                                     // speculative
+        OC_CUDA(cudaEventSynchronize(g2_ev));
+        const double g2 = h_scal[0];
         if (g2 * eps < g2) {
-            enqueue_cg_iter(h, 0);
             for (;;) {
                 if (it + 1 < max_cg) enqueue_cg_iter(h, it + 1);   // speculative
                 OC_CUDA(cudaEventSynchronize(cg_ev[it]));
@@ -846,7 +848,6 @@ struct Problem final : CtxBase {
                 ++it;
                 if (!(g2 * eps < r2) || it >= max_cg) break;
             }
-            sync();   // the gated no-op iteration (if any) must drain before S is consumed elsewhere
         }
         account_hess(h, uint64_t(it));
         cg_iters += uint64_t(it);
