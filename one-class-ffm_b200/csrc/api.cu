@@ -213,7 +213,7 @@ struct Problem final : CtxBase {
     DevBuf<uint32_t> t_rowptr, t_idx, topk_ids, cold_ids, part_id;
     DevBuf<T> part_score, ev_Pva, ev_Qva, ev_at, ev_bt, ev_t1, ev_t2;
     DevBuf<float> tc_phi, tc_plo, tc_qhi, tc_qlo, tc_cand_score;
-    DevBuf<uint32_t> tc_cand_id;
+    DevBuf<uint32_t> tc_cand_id, tc_row_thr;
     bool cold_ready = false;
     bool eval_tc = true;   // OCFFM_EVAL_TC=0 forces the SIMT scorer
     DevBuf<uint8_t> t_cold;
@@ -1109,11 +1109,12 @@ struct Problem final : CtxBase {
                 const size_t slots = size_t(mt) * nsplit * score_topk_tc_cand_slots();
                 tc_cand_score.ensure(slots);
                 tc_cand_id.ensure(slots);
+                tc_row_thr.ensure(mt);
                 part_score.ensure(size_t(mt) * nsplit * 80);
                 part_id.ensure(size_t(mt) * nsplit * 80);
                 score_topk_tc(tc_phi.p, tc_plo.p, mt, tc_qhi.p, tc_qlo.p, n, Kc, bt.p, t_row0, t_row1,
                               uint32_t(n_ranked), t_cold.p, nsplit, tc_cand_score.p, tc_cand_id.p,
-                              part_score.p, part_id.p, st);
+                              part_score.p, part_id.p, tc_row_thr.p, st);
                 merge_topk<float>(part_score.p, part_id.p, nsplit, t_row0, t_row1, topk_ids.p, st);
                 used_tc = true;
             }

@@ -17,6 +17,8 @@
 // by k_merge_topk.  Exactness: an item is dropped only if 80 better ones are already known.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -66,6 +68,32 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// same load delivered to the same shared-memory offsets (data and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                               int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0),
+        "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row atoms of 1024 B (SBO), sm_100 version bit
 __device__ __forceinline__ uint64_t make_desc(const void *smem_tile) {
     uint64_t d = 0;
@@ -116,6 +144,14 @@ __device__ __forceinline__ float key_score(uint64_t k) {
     return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
 }
 __device__ __forceinline__ uint32_t key_id(uint64_t k) { return ~uint32_t(k); }
+// float <-> monotone uint32 (0 is below every finite score): the cross-CTA row thresholds
+__device__ __forceinline__ uint32_t ord_of(float sc) {
+    const uint32_t u = __float_as_uint(sc);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
 
 // Warp-cooperative compaction of one row's candidate buffer (count <= CAP) to its exact top-80 in
 // (score desc, id asc) order: an in-register bitonic sort of KPL keys per lane (element
@@ -207,14 +243,21 @@ struct SmemTC<true> {
     uint32_t tmem_base;
 };
 
-template <bool RESA>
+// MC = 2: the kernel runs as clusters of two CTAs (two row tiles, same item range).  Rank 0 loads
+// every B_hi K-block, rank 1 every B_lo K-block, each with TMA multicast into BOTH CTAs' rings, so
+// the L2->SM operand stream -- the bound of this kernel -- is halved.  A stage is refilled only
+// after both CTAs' MMAs have retired it: the stage-empty barriers count two multicast commits.
+template <bool RESA, int MC>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 uint32_t Kc, const float *__restrict__ bt, uint32_t row0, uint32_t row1, uint32_t n_ranked,
                 uint32_t items_per_split, uint32_t nsplit, const uint8_t *__restrict__ cold,
                 float *__restrict__ cand_score, uint32_t *__restrict__ cand_id,
-                float *__restrict__ part_score, uint32_t *__restrict__ part_id) {
+                float *__restrict__ part_score, uint32_t *__restrict__ part_id, uint32_t *row_thr,
+                uint32_t dbg) {
+    // dbg (OCFFM_TC_DEBUG, measurements only): bit 0 = no row is live (no appends / compactions),
+    // bit 1 = the epilogue does not even read the accumulators
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles must start on 1024-byte boundaries of the shared window
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -227,8 +270,9 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t ntiles = j_hi > j_lo ? (j_hi - j_lo + TN - 1) / TN : 0;
     const uint32_t nkb = Kc / BK;
 
+    const uint32_t crank = MC > 1 ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], MC); }
         for (int s = 0; s < NACC; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 4); }
         mbar_init(&sm.afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,6 +285,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC > 1) cluster_sync_all();   // the partner's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = sm.tmem_base;
 
@@ -265,8 +310,14 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         tma_load_2d(sm.a_hi[s], &map_a_hi, &sm.full[s], int(kb * BK), int(u0));
                         tma_load_2d(sm.a_lo[s], &map_a_lo, &sm.full[s], int(kb * BK), int(u0));
                     }
-                    tma_load_2d(sm.b_hi[s], &map_b_hi, &sm.full[s], int(kb * BK), j0);
-                    tma_load_2d(sm.b_lo[s], &map_b_lo, &sm.full[s], int(kb * BK), j0);
+                    if (MC == 1) {
+                        tma_load_2d(sm.b_hi[s], &map_b_hi, &sm.full[s], int(kb * BK), j0);
+                        tma_load_2d(sm.b_lo[s], &map_b_lo, &sm.full[s], int(kb * BK), j0);
+                    } else if (crank == 0) {
+                        tma_load_2d_mc(sm.b_hi[s], &map_b_hi, &sm.full[s], int(kb * BK), j0, uint16_t(0x3));
+                    } else {
+                        tma_load_2d_mc(sm.b_lo[s], &map_b_lo, &sm.full[s], int(kb * BK), j0, uint16_t(0x3));
+                    }
                 }
             }
         }
@@ -294,7 +345,9 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         umma_tf32(d, ah + adv, bl + adv, 1u);
                         umma_tf32(d, al + adv, bh + adv, 1u);
                     }
-                    umma_commit(&sm.empty[s]);            // smem stage reusable once these MMAs retire
+                    // smem stage reusable once these MMAs retire (in both CTAs when clustered)
+                    if (MC == 1) umma_commit(&sm.empty[s]);
+                    else umma_commit_mc(&sm.empty[s], uint16_t(0x3));
                 }
                 umma_commit(&sm.tfull[acc]);              // accumulator complete
             }
@@ -303,7 +356,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
         const int q = warp & 3, ew = warp - 2;
         const uint32_t row = u0 + uint32_t(q) * 32u + uint32_t(lane);
-        const bool live = row < row1 && !(cold && cold[row]);
+        const bool live = row < row1 && !(cold && cold[row]) && !(dbg & 1u);
         const size_t slot = (size_t(row) * nsplit + blockIdx.y);
         float *cs = cand_score + slot * CAP;
         uint32_t *ci = cand_id + slot * CAP;
@@ -312,6 +365,12 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (uint32_t t = 0; t < ntiles; ++t) {
             const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             const uint32_t j0 = j_lo + t * TN;
+            // Another CTA working on a different item range of the same row may already know 80 items
+            // better than anything seen here: its 80th score is a valid bound for this row too.
+            if (live) {
+                const uint32_t g = __ldcg(row_thr + row);
+                if (g) th = fmaxf(th, ord_to_float(g));
+            }
             mbar_wait(&sm.tfull[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + acc * TN + (uint32_t(q * 32) << 16);
@@ -321,7 +380,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 bnext = j < j_hi ? bt[j] : -INFINITY;
             }
 #pragma unroll 1
-            for (int c0 = 0; c0 < TN; c0 += 32) {
+            for (int c0 = 0; c0 < ((dbg & 2u) ? 0 : TN); c0 += 32) {
                 // make room: a chunk can add at most 32 candidates to a row
                 uint32_t need = __ballot_sync(0xffffffffu, count > CAP - 32);
                 while (need) {
@@ -334,7 +393,10 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const int n = compact_row(rcs, rci, rc, &nth);
                     if (lane == l) {
                         count = n;
-                        if (n == TOP) th = nth;
+                        if (n == TOP) {
+                            th = fmaxf(th, nth);
+                            atomicMax(row_thr + row, ord_of(th));   // publish to the row's other item ranges
+                        }
                     }
                     __syncwarp();
                 }
@@ -395,6 +457,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ---- teardown ----
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC > 1) cluster_sync_all();   // nobody leaves while the partner may still signal its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(NACC * TN)) : "memory");
     }
@@ -463,24 +526,49 @@ void split_tf32(const float *x, float *hi, float *lo, uint64_t n, cudaStream_t s
 void score_topk_tc(const float *Phi, const float *Plo, uint64_t p_rows, const float *Qhi, const float *Qlo,
                    uint64_t q_rows, uint32_t Kc, const float *bt, uint32_t row0, uint32_t row1,
                    uint32_t n_ranked, const uint8_t *cold, uint32_t nsplit, float *cand_score,
-                   uint32_t *cand_id, float *part_score, uint32_t *part_id, cudaStream_t s) {
+                   uint32_t *cand_id, float *part_score, uint32_t *part_id, uint32_t *row_thr, cudaStream_t s) {
     if (row1 <= row0) return;
+    OC_CUDA(cudaMemsetAsync(row_thr + row0, 0, size_t(row1 - row0) * sizeof(uint32_t), s));
     const CUtensorMap ma_hi = make_map(Phi, p_rows, Kc), ma_lo = make_map(Plo, p_rows, Kc);
     const CUtensorMap mb_hi = make_map(Qhi, q_rows, Kc), mb_lo = make_map(Qlo, q_rows, Kc);
     const uint32_t item_tiles = (n_ranked + TN - 1) / TN;
     const uint32_t per = ((item_tiles + nsplit - 1) / nsplit) * TN;
-    const dim3 grid(unsigned((uint64_t(row1 - row0) + TM - 1) / TM), nsplit);
-    if (Kc / BK <= MAX_RES_KB) {
-        const size_t smem = sizeof(SmemTC<true>) + 1024;
-        OC_CUDA(cudaFuncSetAttribute(k_score_topk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        OC_LAUNCH(k_score_topk_tc<true>, grid, kThreadsTC, smem, s, ma_hi, ma_lo, mb_hi, mb_lo, Kc, bt, row0, row1,
-                  n_ranked, per, nsplit, cold, cand_score, cand_id, part_score, part_id);
-    } else {
-        const size_t smem = sizeof(SmemTC<false>) + 1024;
-        OC_CUDA(cudaFuncSetAttribute(k_score_topk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        OC_LAUNCH(k_score_topk_tc<false>, grid, kThreadsTC, smem, s, ma_hi, ma_lo, mb_hi, mb_lo, Kc, bt, row0, row1,
-                  n_ranked, per, nsplit, cold, cand_score, cand_id, part_score, part_id);
+    unsigned tiles = unsigned((uint64_t(row1 - row0) + TM - 1) / TM);
+    static int use_mc = -1;
+    if (use_mc < 0) {
+        const char *e = getenv("OCFFM_EVAL_MC");
+        use_mc = e ? atoi(e) : 2;
     }
+    const int mc = (use_mc >= 2 && tiles >= 2) ? 2 : 1;
+    if (mc == 2) tiles = (tiles + 1) / 2 * 2;   // a padding CTA (all rows dead) keeps the pair complete
+    const bool resa = Kc / BK <= MAX_RES_KB;
+    const size_t smem = (resa ? sizeof(SmemTC<true>) : sizeof(SmemTC<false>)) + 1024;
+    static int dbg = -1;
+    if (dbg < 0) {
+        const char *e = getenv("OCFFM_TC_DEBUG");
+        dbg = e ? atoi(e) : 0;
+    }
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, uint32_t, const float *, uint32_t, uint32_t,
+                 uint32_t, uint32_t, uint32_t, const uint8_t *, float *, uint32_t *, float *, uint32_t *, uint32_t *,
+                 uint32_t) =
+        resa ? (mc == 2 ? k_score_topk_tc<true, 2> : k_score_topk_tc<true, 1>)
+             : (mc == 2 ? k_score_topk_tc<false, 2> : k_score_topk_tc<false, 1>);
+    OC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles, nsplit);
+    cfg.blockDim = dim3(kThreadsTC);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(mc);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OC_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, Kc, bt, row0, row1, n_ranked, per, nsplit,
+                               cold, cand_score, cand_id, part_score, part_id, row_thr, uint32_t(dbg)));
+    count_launch();
 }
 
 }  // namespace ocffm

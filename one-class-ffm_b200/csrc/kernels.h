@@ -200,7 +200,7 @@ void split_tf32(const float *x, float *hi, float *lo, uint64_t n, cudaStream_t s
 void score_topk_tc(const float *Phi, const float *Plo, uint64_t p_rows, const float *Qhi, const float *Qlo,
                    uint64_t q_rows, uint32_t Kc, const float *bt, uint32_t row0, uint32_t row1,
                    uint32_t n_ranked, const uint8_t *cold, uint32_t nsplit, float *cand_score,
-                   uint32_t *cand_id, float *part_score, uint32_t *part_id, cudaStream_t s);
+                   uint32_t *cand_id, float *part_score, uint32_t *part_id, uint32_t *row_thr, cudaStream_t s);
 
 // top-80 of a plain score vector (the `popular` ranking shared by all cold rows)
 template <typename T>
