@@ -360,6 +360,9 @@ def main():
                     sec_per_outer_iteration=sec / args.steps, cg_iters_per_step=st.cg_iters / args.steps,
                     objective=objective, gpu_launches=int(st.kernel_launches), e2e=e2e, roofline=roofline,
                     cpu_baseline=cpu, eval=eval_info, clocks=sampler.summary(), datagen_s=t_gen)
+        if int(os.environ.get("OCFFM_PROFILE", "1")) >= 2:      # diagnostic runs only (event timers per phase)
+            line["phases_ms_per_step"] = {f: getattr(st, "ms_" + f) / args.steps for f in (
+                "side_grad", "side_cg", "side_update", "cross_grad", "cross_cg", "cross_update")}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -93,13 +93,99 @@ ncclDataType_t nccl_type<double>() { return ncclDouble; }
 struct Comm {
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
+    // peer-memory path (peer.cu) for messages up to pv.cap bytes; NCCL carries the rest
+    bool peer_ok = false;
+    PeerView pv{};
+    int *peer_err_host = nullptr;
+    std::vector<void *> opened;
+    unsigned long long seq = 0;
+    uint64_t peer_calls = 0, nccl_calls = 0;
+
     ~Comm() {
+        for (void *p : opened) cudaIpcCloseMemHandle(p);
+        if (pv.base[rank]) cudaFree(pv.base[rank]);
+        if (peer_err_host) cudaFreeHost(peer_err_host);
         if (comm) Nccl::get().CommDestroy(comm);
     }
     bool active() const { return nranks > 1; }
+
+    // Maps every rank's staging area into this process (CUDA IPC; the ranks of one node).  Any
+    // failure on any rank leaves the whole job on NCCL: the decision is all-reduced.
+    void peer_setup(cudaStream_t s) {
+        if (!active() || nranks > kPeerMaxRanks) return;
+        if (const char *e = getenv("OCFFM_PEER")) if (atoi(e) == 0) return;
+        size_t cap = size_t(512) << 10;
+        if (const char *e = getenv("OCFFM_PEER_CAP_KB")) cap = size_t(std::max(1, atoi(e))) << 10;
+        struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+        static_assert(sizeof(Msg) == 80, "handle message layout");
+        Msg mine{};
+        mine.ok = 1;
+        unsigned char *area = nullptr;
+        const size_t bytes = peer_area_bytes(nranks, cap);
+        if (cudaMalloc(&area, bytes) != cudaSuccess) mine.ok = 0;
+        if (mine.ok && cudaMemsetAsync(area, 0, bytes, s) != cudaSuccess) mine.ok = 0;
+        if (mine.ok && cudaIpcGetMemHandle(&mine.h, area) != cudaSuccess) mine.ok = 0;
+        if (mine.ok && cudaHostAlloc(&peer_err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) mine.ok = 0;
+        cudaGetLastError();
+        DevBuf<unsigned char> x;
+        x.alloc(sizeof(Msg) * nranks);
+        OC_CUDA(cudaMemcpyAsync(x.p + sizeof(Msg) * rank, &mine, sizeof(Msg), cudaMemcpyHostToDevice, s));
+        Nccl &n = Nccl::get();
+        OC_NCCL(n.GroupStart());
+        for (int q = 0; q < nranks; ++q)
+            OC_NCCL(n.Broadcast(x.p + sizeof(Msg) * q, x.p + sizeof(Msg) * q, sizeof(Msg), ncclChar, q, comm, s));
+        OC_NCCL(n.GroupEnd());
+        std::vector<Msg> all(nranks);
+        OC_CUDA(cudaMemcpyAsync(all.data(), x.p, sizeof(Msg) * nranks, cudaMemcpyDeviceToHost, s));
+        OC_CUDA(cudaStreamSynchronize(s));
+        bool ok = true;
+        for (int q = 0; q < nranks; ++q) ok = ok && all[q].ok;
+        pv.nranks = nranks;
+        pv.rank = rank;
+        pv.cap = cap;
+        pv.base[rank] = area;
+        if (ok) {
+            for (int q = 0; q < nranks && ok; ++q) {
+                if (q == rank) continue;
+                void *p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    ok = false;
+                    cudaGetLastError();
+                } else {
+                    opened.push_back(p);
+                    pv.base[q] = static_cast<unsigned char *>(p);
+                }
+            }
+            if (ok) {
+                *peer_err_host = 0;
+                ok = cudaHostGetDevicePointer(reinterpret_cast<void **>(&pv.error), peer_err_host, 0) == cudaSuccess;
+            }
+        }
+        // every rank must take the same path
+        DevBuf<float> agree;
+        agree.alloc(1);
+        const float v = ok ? 1.0f : 0.0f;
+        OC_CUDA(cudaMemcpyAsync(agree.p, &v, sizeof(float), cudaMemcpyHostToDevice, s));
+        OC_NCCL(n.AllReduce(agree.p, agree.p, 1, ncclFloat, ncclSum, comm, s));
+        float total = 0;
+        OC_CUDA(cudaMemcpyAsync(&total, agree.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+        OC_CUDA(cudaStreamSynchronize(s));
+        peer_ok = total == float(nranks);
+    }
+    void check_peer() {
+        if (peer_ok && *static_cast<volatile int *>(peer_err_host))
+            throw Error(OCFFM_E_COMM, "peer all-reduce timed out waiting for another rank");
+    }
+
     template <typename T>
     void allreduce(T *buf, size_t n, cudaStream_t s) {
         if (!active() || !n) return;
+        if (peer_ok && n * sizeof(T) <= pv.cap) {
+            ++peer_calls;
+            peer_allreduce<T>(pv, buf, n, ++seq, s);
+            return;
+        }
+        ++nccl_calls;
         OC_NCCL(Nccl::get().AllReduce(buf, buf, n, nccl_type<T>(), ncclSum, comm, s));
     }
     // all-gather of row slices with unequal sizes: rank q owns rows [lo(q), lo(q+1)) of a
@@ -300,7 +386,10 @@ struct Problem final : CtxBase {
 
     // index_vec, ffm.cpp:53-55
     size_t bidx(uint32_t f1, uint32_t f2) const { return f2 + size_t(f - 1) * f1 - size_t(f1) * (f1 - 1) / 2; }
-    void sync() { OC_CUDA(cudaStreamSynchronize(st)); }
+    void sync() {
+        OC_CUDA(cudaStreamSynchronize(st));
+        comm.check_peer();
+    }
     void bind() {
         OC_CUDA(cudaSetDevice(device));
         g_launch_counter = &launches;
@@ -324,6 +413,7 @@ struct Problem final : CtxBase {
             ncclUniqueId uid;
             memcpy(&uid, id, sizeof(uid));
             OC_NCCL(Nccl::get().CommInitRank(&comm.comm, nranks, uid, rank));
+            comm.peer_setup(st);
         }
     }
     uint32_t lo(uint64_t rows) const { return uint32_t(rows * comm.rank / comm.nranks); }
@@ -858,14 +948,12 @@ struct Problem final : CtxBase {
     void apply_update(const Half &h) {
         const size_t s = sizeof(T);
         const uint64_t len = h.D * kp, nnzY = h.Yown->nnz, nnzX = h.X->nnz;
-        if (h.sliced) {
-            axpy<T>(h.W1 + h.soff() * kp, S.p + h.soff() * kp, T(1), (h.s1 - h.s0) * kp, st);
-            comm.allgather_rows(h.W1, h.D, kp, st);   // once per half solve: replicas of W stay whole
-        } else {
-            axpy<T>(h.W1, S.p, T(1), len, st);
-        }
+        // sliced half: one all-gather of the step per half solve, then every rank applies the whole
+        // step to its replicas (W, P, a) with the single-rank kernels
+        if (h.sliced) comm.allgather_rows(S.p, h.D, kp, st);
+        axpy<T>(h.W1, S.p, T(1), len, st);
         const T *q_side = h.side ? h.Q1 : nullptr;
-        if (!comm.active()) {
+        if (!comm.active() || h.sliced) {
             spmm_update<T>(h.X->view_all(), S.p, XS.p, h.P1, h.ldp, q_side, gap.p, h.a1, kp, st);
         } else {
             spmm_rows<T>(h.X->view(), S.p, XS.p, kp, kp, st);

@@ -214,4 +214,20 @@ void eval_metrics(const uint32_t *ids, const uint32_t *cold_ids80, const uint8_t
                   const T *popular, uint32_t n_items, uint32_t n_ranked, double *acc64,
                   cudaStream_t s);
 
+// ---- peer.cu: one-shot all-reduce over NVLink peer memory (small messages of the sharded solver) ---
+constexpr int kPeerMaxRanks = 16;
+constexpr int kPeerMaxBlocks = 64;
+constexpr int kPeerThreads = 256;
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+struct PeerView {
+    unsigned char *base[kPeerMaxRanks];   // every rank's staging area, mapped here (base[rank] is local)
+    int nranks, rank;
+    size_t cap;                           // largest message in bytes; a [slot][src] region is 2*cap
+    int *error;                           // local flag: set when a wait timed out
+};
+inline size_t peer_area_bytes(int nranks, size_t cap) { return size_t(2) * nranks * cap * 2; }
+// buf[0:n] <- sum over ranks, in rank order, identical bits everywhere; seq: 1, 2, 3, ... per call
+template <typename T>
+void peer_allreduce(const PeerView &pv, T *buf, size_t n, unsigned long long seq, cudaStream_t s);
+
 }  // namespace ocffm
