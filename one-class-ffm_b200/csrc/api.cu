@@ -255,6 +255,13 @@ struct Problem final : CtxBase {
     uint32_t chunk = 64;
     bool diag_fast = true;      // OCFFM_DIAG_FAST=0 disables the fused same-side CG pass
     bool slice_cg = true;       // OCFFM_SLICE_CG=0: always replicate CG vectors across ranks
+    // The reference keeps two copies of y-tilde (by user and by item, ffm.cpp:393,400) and adds every
+    // update to both with the same arithmetic, so they stay bit-identical.  On one GPU the update
+    // is applied to the orientation being swept only and the other one is refreshed by a permuted
+    // copy right before it is next read (4 bytes gathered per entry instead of a d-wide row).
+    // OCFFM_MIRROR_YT=0 updates both copies as the reference does; multi-rank runs always do
+    // (each rank owns different slices of the two orientations).
+    bool mirror_yt = false, mirror_allowed = true;
     uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
     bool profile = false;
 
@@ -281,6 +288,8 @@ struct Problem final : CtxBase {
         uint32_t n_items = 0, row0 = 0, row1 = 0;
         DevBuf<uint32_t> rowptr, idx, wi_row, wi_beg, wi_cnt;
         DevBuf<T> yt;
+        DevBuf<uint32_t> mirror_pos;      // position of each entry in the other orientation (mirror_yt)
+        bool fresh = true;                // yt holds every update made so far
         std::vector<uint64_t> h_rowptr;   // kept for get_csc / stats
         std::vector<uint32_t> h_idx;
         OmegaView<T> view() const {
@@ -359,6 +368,7 @@ struct Problem final : CtxBase {
             }
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
         if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_MIRROR_YT")) mirror_allowed = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_SLICE_CG")) slice_cg = atoi(e) != 0;
@@ -557,7 +567,36 @@ struct Problem final : CtxBase {
         OC_REQUIRE(cp[n] == nnz, "labels >= number of items are not supported (the reference leaves "
                                  "its two copies of Y inconsistent, ffm.cpp:267-268)");
         build_omega(YV, n, cp, ri);
+        mirror_yt = false;
+        if (!comm.active() && mirror_allowed && nnz) {
+            // entry t of the CSR <-> entry pos of the CSC; needs the columns listed by ascending user
+            std::vector<uint32_t> u2v(nnz), v2u(nnz);
+            std::vector<uint64_t> cur(cp, cp + n);
+            bool ok = true;
+            for (uint64_t i = 0; i < m && ok; ++i)
+                for (uint64_t t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+                    const uint64_t pos = cur[idx[t]]++;
+                    if (pos >= cp[idx[t] + 1] || ri[pos] != i) { ok = false; break; }
+                    u2v[t] = uint32_t(pos);
+                    v2u[pos] = uint32_t(t);
+                }
+            if (ok) {
+                YU.mirror_pos.upload(u2v, st);
+                YV.mirror_pos.upload(v2u, st);
+                sync();
+                mirror_yt = true;
+            }
+        }
+        YU.fresh = YV.fresh = true;
         state_ready = false;
+    }
+    // make Y.yt current before it is read or updated in place
+    void freshen(Omega &Y) {
+        if (!mirror_yt || Y.fresh) return;
+        Omega &other = &Y == &YU ? YV : YU;
+        gather_copy<T>(Y.yt.p, other.yt.p, Y.mirror_pos.p, Y.nnz, st);
+        algo_bytes += Y.nnz * (4 + 2 * sizeof(T));
+        Y.fresh = true;
     }
 
     void set_test_labels(uint64_t mt_, const uint64_t *rowptr, const uint32_t *idx,
@@ -719,6 +758,7 @@ struct Problem final : CtxBase {
             sddmm_add<T>(YU.view(), Pc.p + size_t(p) * kp, Kc, Qc.p + size_t(p) * kp, Kc, kp, st);
             sddmm_add<T>(YV.view(), Qc.p + size_t(p) * kp, Kc, Pc.p + size_t(p) * kp, Kc, kp, st);
         }
+        YU.fresh = YV.fresh = true;
         sync();
         state_ready = true;
     }
@@ -806,6 +846,7 @@ struct Problem final : CtxBase {
         const size_t s = sizeof(T);
         OC_CUDA(cudaMemsetAsync(G.p, 0, h.D * kp * sizeof(T), st));
         if (h.X->n_hot) h.X->shadow.zero(st);
+        freshen(*h.Yown);
         const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
         if (h.side) {
             OC_CUDA(cudaMemsetAsync(ysum.p, 0, h.m1 * sizeof(T), st));
@@ -961,19 +1002,23 @@ struct Problem final : CtxBase {
             // P1 += XS (and the side terms) on every rank's replica
             spmm_update_from_xs(h, q_side);
         }
+        freshen(*h.Yown);
+        const uint64_t copies = mirror_yt ? 1 : 2;
+        if (mirror_yt) h.Yoth->fresh = false;
         if (h.side) {
             ytilde_add_gap<T>(h.Yown->view(), gap.p, 1, st);
-            ytilde_add_gap<T>(h.Yoth->view(), gap.p, 0, st);
+            if (!mirror_yt) ytilde_add_gap<T>(h.Yoth->view(), gap.p, 0, st);
             algo_bytes += 3 * h.D * k * s + nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) +
-                          4 * h.m1 * k * s + 2 * (nnzY * (4 + 2 * s) + h.m1 * s);
+                          4 * h.m1 * k * s + copies * (nnzY * (4 + 2 * s) + h.m1 * s);
         } else {
             sddmm_add<T>(h.Yown->view(), XS.p, kp, h.Q1, h.ldq, kp, st);
-            sddmm_add<T>(h.Yoth->view(), h.Q1, h.ldq, XS.p, kp, kp, st);
+            if (!mirror_yt) sddmm_add<T>(h.Yoth->view(), h.Q1, h.ldq, XS.p, kp, kp, st);
             algo_bytes += 3 * h.D * k * s + nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) +
                           4 * h.m1 * k * s +
-                          2 * (nnzY * (4 + 2 * s) + gather_bytes(h.m1 * k * s, nnzY, k * s) +
-                               gather_bytes(h.n1 * k * s, nnzY, k * s));
+                          copies * (nnzY * (4 + 2 * s)) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
+                          (copies - 1) * gather_bytes(h.m1 * k * s, nnzY, k * s);
         }
+        // the reference's traversal count (both copies, ffm.cpp:423-436, 451-464)
         nnz_trav += 2 * nnzY + nnzX;
     }
     // multi-rank variant of the tail of spmm_update: XS is complete on every rank
@@ -1126,6 +1171,7 @@ struct Problem final : CtxBase {
         reduce_sum<T>(b.p, n, 1, acc64.p + 3, st);
         // Omega part over the local rows of the user orientation
         {
+            freshen(YU);
             const uint64_t b0 = YU.h_rowptr[YU.row0], e0 = YU.h_rowptr[YU.row1];
             omega_objective<T>(YU.yt.p + b0, e0 - b0, T(prm.omega), T(prm.r), acc64.p + 4, st);
         }
@@ -1247,8 +1293,8 @@ struct Problem final : CtxBase {
         else if (s == "b") { src = b.p; cnt = n; }
         else if (s == "sa") { src = sa.p; cnt = m; }
         else if (s == "sb") { src = sb.p; cnt = n; }
-        else if (s == "ytilde_csr") { src = YU.yt.p; cnt = YU.nnz; }
-        else if (s == "ytilde_csc") { src = YV.yt.p; cnt = YV.nnz; }
+        else if (s == "ytilde_csr") { freshen(YU); src = YU.yt.p; cnt = YU.nnz; }
+        else if (s == "ytilde_csc") { freshen(YV); src = YV.yt.p; cnt = YV.nnz; }
         else if (s == "popular") { src = popular.p; cnt = n_ranked; }
         else throw Error(OCFFM_E_INVALID, "unknown vector name " + s);
         if (count) *count = cnt;
@@ -1305,6 +1351,7 @@ struct Problem final : CtxBase {
 // small element-wise helpers used only by the multi-rank update path
 template <typename T>
 __global__ void k_strided_add(T *dst, uint32_t ld, const T *src, uint64_t rows, uint32_t kp) {
+    pdl_enter();
     const uint64_t nvec = rows * (kp / 4);
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -1317,6 +1364,7 @@ __global__ void k_strided_add(T *dst, uint32_t ld, const T *src, uint64_t rows, 
 }
 template <typename T>
 __global__ void k_vec_add(T *y, const T *x, uint64_t n) {
+    pdl_enter();
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x)
         y[i] += x[i];

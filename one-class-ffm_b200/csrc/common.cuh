@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <cstdlib>
 #include <vector>
 
 namespace ocffm {
@@ -34,11 +36,42 @@ extern thread_local uint64_t *g_launch_counter;
 inline void count_launch() {
     if (g_launch_counter) ++*g_launch_counter;
 }
-#define OC_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
-    do {                                                                    \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);         \
-        ::ocffm::count_launch();                                            \
-        OC_CUDA(cudaGetLastError());                                        \
+// Programmatic dependent launch: every kernel of the library starts with pdl_enter(), which waits
+// for the previous grid of the stream to complete (memory visible) and at once lets the NEXT
+// kernel's CTAs be scheduled, so the launch latency and CTA ramp of the ~700 short kernels of an
+// outer iteration overlap the tail of their predecessor.  OCFFM_PDL=0 launches plainly.
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("OCFFM_PDL");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define OC_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+    do {                                                                                    \
+        OC_CUDA(::ocffm::launch_kernel(kernel, (grid), (block), (smem), (stream), __VA_ARGS__)); \
+        ::ocffm::count_launch();                                                            \
     } while (0)
 
 template <typename T>

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(kThreads)
 k_gram(const T *__restrict__ A, uint32_t lda, uint32_t Kc, const T *__restrict__ B, uint32_t ldb,
        uint32_t row0, uint32_t row1, const T *__restrict__ wvec, double *__restrict__ Out64,
        double *__restrict__ colsum64, double *__restrict__ wsum64, uint32_t rows_per_cta) {
+    pdl_enter();
     constexpr int NB = KP / TB;          // threads along the B columns
     constexpr int NA = kThreads / NB;    // threads along the A columns
     constexpr int KCH = NA * TA;         // A columns handled by one CTA (blockIdx.y picks the chunk)
@@ -111,6 +112,7 @@ template <typename T, int KP, int TM, int TN>
 __global__ void __launch_bounds__(kThreads)
 k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restrict__ B,
           T *__restrict__ C, uint64_t M, Gate gate) {
+    pdl_enter();
     constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
     if (!gate_open(gate)) return;
     constexpr int BK = sizeof(T) == 8 ? 16 : 32;   // keeps static shared memory under 48 KB
@@ -186,6 +188,7 @@ inline unsigned ew_blocks(uint64_t n_vec) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_convert(const double *__restrict__ src, T *__restrict__ dst, uint64_t n) {
+    pdl_enter();
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x)
         dst[i] = T(src[i]);
@@ -219,6 +222,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_pad_from_f64(const double *__restrict__ src, T *__restrict__ dst, uint64_t rows, uint32_t k,
                uint32_t ld) {
+    pdl_enter();
     const uint64_t n = rows * ld;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -232,6 +236,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_unpad_to_f64(const T *__restrict__ src, uint32_t ld, double *__restrict__ dst, uint64_t rows,
                uint32_t k) {
+    pdl_enter();
     const uint64_t n = rows * k;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(kThreads)
 k_cg_init(T *__restrict__ G, const T *__restrict__ W, const T *__restrict__ freq, T lambda,
           T *__restrict__ R, T *__restrict__ V, T *__restrict__ S, uint64_t nvec, int kp4,
           SolveScalars *sc) {
+    pdl_enter();
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -267,6 +273,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_dir(T *__restrict__ V, const T *__restrict__ R, T *__restrict__ Hv, uint64_t nvec, int it,
          const SolveScalars *sc) {
+    pdl_enter();
     if (!gate_open(Gate{sc, it})) return;
     const T beta = it > 0 ? T(sc->r2[it] / sc->r2[it - 1]) : T(0);
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -285,6 +292,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_reg_dot(T *__restrict__ Hv, const T *__restrict__ V, const T *__restrict__ freq, T lambda,
              uint64_t nvec, int kp4, int it, SolveScalars *sc, int gated) {
+    pdl_enter();
     if (gated && !gate_open(Gate{sc, it})) return;
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -303,6 +311,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T *__restrict__ Hv,
           uint64_t nvec, int it, SolveScalars *sc) {
+    pdl_enter();
     if (!gate_open(Gate{sc, it})) return;
     const T alpha = T(sc->r2[it] / sc->vHv[it]);
     double local = 0;
@@ -322,6 +331,7 @@ k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_axpy(T *__restrict__ y, const T *__restrict__ x, T alpha, uint64_t nvec) {
+    pdl_enter();
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
         V4<T> a = ld4(y + i * 4);
@@ -334,6 +344,7 @@ k_axpy(T *__restrict__ y, const T *__restrict__ x, T alpha, uint64_t nvec) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_reduce_sum(const T *__restrict__ x, uint64_t n, int square, double *out64) {
+    pdl_enter();
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -349,6 +360,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_col_sums(const T *__restrict__ A, uint32_t lda, uint32_t cols, uint32_t row0, uint32_t row1,
            double *out64, uint32_t rows_per_cta) {
+    pdl_enter();
     const uint64_t rbeg = uint64_t(row0) + uint64_t(blockIdx.x) * rows_per_cta;
     const uint64_t rend = min(uint64_t(row1), rbeg + rows_per_cta);
     const uint32_t lanes_per_row = min(cols, uint32_t(kThreads));
@@ -366,6 +378,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_matvec_rows(const T *__restrict__ A, uint32_t lda, uint32_t cols, uint32_t rows,
               const T *__restrict__ v, T *__restrict__ out) {
+    pdl_enter();
     const uint64_t row = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -378,6 +391,7 @@ k_matvec_rows(const T *__restrict__ A, uint32_t lda, uint32_t cols, uint32_t row
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_omega_objective(const T *__restrict__ yt, uint64_t nnz, T w, T r, double *out64) {
+    pdl_enter();
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -487,6 +501,22 @@ void axpy(T *y, const T *x, T alpha, uint64_t n, cudaStream_t s) {
     if (!n) return;
     OC_LAUNCH((k_axpy<T>), ew_blocks(n / 4), kThreads, 0, s, y, x, alpha, n / 4);
 }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_gather_copy(T *__restrict__ dst, const T *__restrict__ src, const uint32_t *__restrict__ pos, uint64_t n) {
+    pdl_enter();
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x)
+        dst[i] = __ldg(src + pos[i]);
+}
+template <typename T>
+void gather_copy(T *dst, const T *src, const uint32_t *pos, uint64_t n, cudaStream_t s) {
+    if (!n) return;
+    OC_LAUNCH((k_gather_copy<T>), ew_blocks(n), kThreads, 0, s, dst, src, pos, n);
+}
+template void gather_copy<float>(float *, const float *, const uint32_t *, uint64_t, cudaStream_t);
+template void gather_copy<double>(double *, const double *, const uint32_t *, uint64_t, cudaStream_t);
 
 template <typename T>
 void reduce_sum(const T *x, uint64_t n, int square, double *out64, cudaStream_t s) {

@@ -106,6 +106,7 @@ k_score_topk(const T *__restrict__ Pva, const T *__restrict__ Qva, uint32_t Kc,
              const T *__restrict__ bt, uint32_t row0, uint32_t row1, uint32_t n_ranked,
              uint32_t items_per_split, uint32_t nsplit, const uint8_t *__restrict__ cold,
              T *__restrict__ part_score, uint32_t *__restrict__ part_id) {
+    pdl_enter();
     constexpr int BK = 32;
     constexpr int NA = TU * (BK / 4) / kThreads;   // float4 loads per thread for the row tile (2)
     constexpr int NB = TI * (BK / 4) / kThreads;   // ... for the item tile (4)
@@ -247,6 +248,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_merge_topk(const T *__restrict__ part_score, const uint32_t *__restrict__ part_id, uint32_t nsplit,
              uint32_t row0, uint32_t row1, uint32_t *__restrict__ ids) {
+    pdl_enter();
     const uint64_t row = uint64_t(row0) + ((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31u;
     if (row >= row1) return;
@@ -276,6 +278,7 @@ k_merge_topk(const T *__restrict__ part_score, const uint32_t *__restrict__ part
 template <typename T>
 __global__ void __launch_bounds__(32)
 k_vector_topk(const T *__restrict__ z, uint32_t n_ranked, uint32_t *__restrict__ ids80) {
+    pdl_enter();
     __shared__ T sc[TOP];
     __shared__ uint32_t id[TOP];
     TopList<T> L{sc, id};
@@ -302,6 +305,7 @@ k_eval_metrics(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ co
                const T *__restrict__ Pva, const T *__restrict__ Qva, uint32_t Kc,
                const T *__restrict__ at, const T *__restrict__ bt, const T *__restrict__ popular,
                uint32_t n_items, uint32_t n_ranked, double *__restrict__ acc64) {
+    pdl_enter();
     const uint64_t row = uint64_t(row0) + ((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31u;
     if (row >= row1) return;

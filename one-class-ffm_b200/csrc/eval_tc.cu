@@ -466,6 +466,7 @@ k_score_topk_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 // X -> (hi, lo): hi = round-to-nearest TF32 of x, lo = x - hi (exact in fp32)
 __global__ void __launch_bounds__(256)
 k_split_tf32(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, uint64_t n) {
+    pdl_enter();
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
         const float v = x[i];
         uint32_t h;

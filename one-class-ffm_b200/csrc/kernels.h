@@ -162,6 +162,9 @@ void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScala
              cudaStream_t s);
 template <typename T>
 void axpy(T *y, const T *x, T alpha, uint64_t n, cudaStream_t s);
+// dst[i] = src[pos[i]]: refreshes one orientation of the y-tilde cache from the other
+template <typename T>
+void gather_copy(T *dst, const T *src, const uint32_t *pos, uint64_t n, cudaStream_t s);
 // out64 += sum(x) / sum(x*x) / colsum of a [rows x ld] matrix
 template <typename T>
 void reduce_sum(const T *x, uint64_t n, int square, double *out64, cudaStream_t s);

@@ -67,6 +67,7 @@ __device__ __forceinline__ void unpack(float *buf, uint32_t i, uint32_t n, const
 template <typename T>
 __global__ void __launch_bounds__(kPeerThreads)
 k_peer_allreduce(PeerView pv, T *__restrict__ buf, uint32_t n, uint32_t n_lines, uint32_t seq) {
+    pdl_enter();
     using Acc = typename std::conditional<sizeof(T) == 8, Acc64, Acc32>::type;
     const int slot = int(seq & 1u);
     const uint32_t stride = gridDim.x * blockDim.x;

@@ -58,6 +58,7 @@ __device__ __forceinline__ V4<T> scale4(const V4<T> &v, T s) {
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads)
 k_spmm_rows(CsrView<T> X, const T *__restrict__ A, T *__restrict__ C, uint32_t ldc) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     const uint32_t lg = threadIdx.x % G;
@@ -74,6 +75,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads)
 k_spmm_update(CsrView<T> X, const T *__restrict__ S, T *__restrict__ XS, T *__restrict__ P1,
               uint32_t ldp, const T *__restrict__ Q1side, T *__restrict__ gap, T *__restrict__ a1) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     const uint32_t lg = threadIdx.x % G;
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
              const T *__restrict__ Tm, const T *__restrict__ a1, const T *__restrict__ oQ,
              const T *__restrict__ bQ, T w, T r, T *__restrict__ Gout) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (item >= Y.n_items) return;
@@ -155,6 +158,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
              const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     constexpr int U = G < 8 ? G : 8;   // gathers kept in flight per lane
     if (!gate_open(gate)) return;
@@ -209,6 +213,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *__restrict__ Vo,
             uint32_t ldv) {
+    pdl_enter();
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (item >= Y.n_items) return;
     const uint32_t lg = threadIdx.x % G;
@@ -251,6 +256,7 @@ k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *_
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads)
 k_ytilde_rowsum(OmegaView<T> Y, T *__restrict__ ysum) {
+    pdl_enter();
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (item >= Y.n_items) return;
     const uint32_t lg = threadIdx.x % G;
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(kThreads)
 k_side_rows(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, const T *__restrict__ a1,
             const T *__restrict__ sa1, const T *__restrict__ ysum, const double *__restrict__ bsum,
             const T *__restrict__ V, T w, T r, T n1, T *__restrict__ Out, Gate gate) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     if (!gate_open(gate)) return;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(kThreads)
 k_side_diag_iter(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__restrict__ V,
                  const T *__restrict__ R, T *__restrict__ Hv, const T *__restrict__ freq, T lambda, T w, T n1,
                  int it, SolveScalars *sc) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     if (!gate_open(Gate{sc, it})) return;
     const T beta = it > 0 ? T(sc->r2[it] / sc->r2[it - 1]) : T(0);
@@ -353,6 +361,7 @@ k_side_diag_iter(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__re
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_ytilde_base(OmegaView<T> Y, const T *__restrict__ a_own, const T *__restrict__ b_oth) {
+    pdl_enter();
     constexpr int G = 8;
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (item >= Y.n_items) return;
@@ -366,6 +375,7 @@ k_ytilde_base(OmegaView<T> Y, const T *__restrict__ a_own, const T *__restrict__
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_ytilde_gap_by_row(OmegaView<T> Y, const T *__restrict__ gap) {
+    pdl_enter();
     constexpr int G = 8;
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (item >= Y.n_items) return;
@@ -379,6 +389,7 @@ k_ytilde_gap_by_row(OmegaView<T> Y, const T *__restrict__ gap) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_ytilde_gap_by_idx(OmegaView<T> Y, const T *__restrict__ gap) {
+    pdl_enter();
     const uint64_t b = Y.rowptr[Y.row0], e = Y.rowptr[Y.row1];
     for (uint64_t t = b + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < e;
          t += uint64_t(gridDim.x) * blockDim.x)
@@ -389,6 +400,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads)
 k_rowwise_dot(const T *__restrict__ P, const T *__restrict__ Q, uint32_t rows, T *__restrict__ out,
               int accumulate) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (g >= rows) return;
@@ -402,6 +414,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads)
 k_fold_hot(const T *__restrict__ shadow, const uint32_t *__restrict__ hot_feat, uint32_t n_hot,
            T *__restrict__ Out) {
+    pdl_enter();
     constexpr uint32_t kp = 4 * G;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (g >= n_hot) return;
