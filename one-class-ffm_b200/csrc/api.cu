@@ -262,6 +262,8 @@ struct Problem final : CtxBase {
     // OCFFM_MIRROR_YT=0 updates both copies as the reference does; multi-rank runs always do
     // (each rank owns different slices of the two orientations).
     bool mirror_yt = false, mirror_allowed = true;
+    // OCFFM_FUSED_DOT=0: separate direction / regulariser+dot kernels per CG iteration (5 instead of 3)
+    bool fused_dot = true;
     uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
     bool profile = false;
 
@@ -276,10 +278,11 @@ struct Problem final : CtxBase {
         bool identity = false;   // diagonal with idx[i] == i: a rank's rows touch only its own feature slice
         uint32_t row0 = 0, row1 = 0;
         CsrView<T> view() const {
-            return {rowptr.p, idx.p, val.p, row0, row1, n_hot ? hot_slot.p : nullptr, shadow.p};
+            return {rowptr.p, idx.p, val.p, row0, row1, n_hot ? hot_slot.p : nullptr, shadow.p, diagonal, identity};
         }
         CsrView<T> view_all() const {
-            return {rowptr.p, idx.p, val.p, 0, uint32_t(rows), n_hot ? hot_slot.p : nullptr, shadow.p};
+            return {rowptr.p, idx.p, val.p, 0, uint32_t(rows), n_hot ? hot_slot.p : nullptr, shadow.p, diagonal,
+                    identity};
         }
     };
     struct Omega {
@@ -369,6 +372,7 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
         if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_MIRROR_YT")) mirror_allowed = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_FUSED_DOT")) fused_dot = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_SLICE_CG")) slice_cg = atoi(e) != 0;
@@ -854,7 +858,7 @@ struct Problem final : CtxBase {
             OC_CUDA(cudaMemsetAsync(&sc->bsum, 0, sizeof(double), st));
             reduce_sum<T>(h.b1, h.n1, 0, &sc->bsum, st);
             side_rows<T>(0, h.Yown->view(), h.X->view(), h.Q1, h.a1, h.sa1, ysum.p, &sc->bsum, nullptr,
-                         T(prm.omega), T(prm.r), T(h.n1), G.p, kp, kNoGate, st);
+                         T(prm.omega), T(prm.r), T(h.n1), G.p, kp, kNoGate, nullptr, st);
             algo_bytes += nnzY * s + h.m1 * (k + 3) * s + nnzX * (4 + s) + 2 * h.D * k * s;
         } else {
             prepare_cross(h);
@@ -890,13 +894,25 @@ struct Problem final : CtxBase {
 
     // Hv (without the regulariser) for the direction in V.  Returns nothing; the caller accounts
     // the statistics with account_hess() once it knows the iteration really ran.
-    void hess_scatter(const Half &h, Gate gate) {
+    // fuse_it >= 0 (solver path): the pass also performs the direction update of CG iteration
+    // fuse_it on the way (cross halves: inside the V * QTQ row GEMM) and adds V . Hv_data to
+    // sc->vHv[fuse_it]; fuse_it < 0: plain Hv of the direction in V.
+    void hess_scatter(const Half &h, Gate gate, int fuse_it = -1) {
         if (h.X->n_hot) h.X->shadow.zero(st);
+        double *dot_out = fuse_it >= 0 ? sc->vpart[fuse_it] : nullptr;
         if (h.side) {
             side_rows<T>(1, h.Yown->view(), h.X->view(), h.Q1, nullptr, nullptr, nullptr, nullptr, V.p,
-                         T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, gate, st);
+                         T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, gate, dot_out, st);
         } else {
-            rowgemm<T>(V.p + h.soff() * kp, kp, kp, qtq_of(h), VQ.p + h.soff() * kp, h.s1 - h.s0, kp, gate, st);
+            const size_t o = h.soff() * kp;
+            if (fuse_it >= 0) {
+                uint64_t lo = 0, hi = h.s1 - h.s0;
+                share_of(h, lo, hi);
+                rowgemm_dir<T>(V.p + o, R.p + o, Hv.p + o, h.freq ? h.freq + h.soff() : nullptr, T(prm.lambda),
+                               lo, hi, qtq_of(h), VQ.p + o, h.s1 - h.s0, kp, fuse_it, sc, st);
+            } else {
+                rowgemm<T>(V.p + o, kp, kp, qtq_of(h), VQ.p + o, h.s1 - h.s0, kp, gate, st);
+            }
             size_t ev = 0;
             if (profile) {
                 if (hv_events_used >= 4096) { sync(); drain_hv_events(); }
@@ -904,11 +920,23 @@ struct Problem final : CtxBase {
                 OC_CUDA(cudaEventRecord(hv_events[ev].first, st));
             }
             hess_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega), Hv.p,
-                               kp, gate, st);
+                               kp, gate, dot_out, st);
             if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
         }
         if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, Hv.p, kp, st);
         if (!h.sliced) comm.allreduce(Hv.p, h.D * kp, st);
+    }
+    // rows (relative to the half's slice) whose lambda c_f |V_f|^2 this rank accounts for: all of a
+    // slice, or a 1/nranks share of a replicated vector (the partial sums are all-reduced)
+    void share_of(const Half &h, uint64_t &lo, uint64_t &hi) const {
+        const uint64_t rows = h.s1 - h.s0;
+        if (comm.active() && !h.sliced) {
+            lo = rows * comm.rank / comm.nranks;
+            hi = rows * (comm.rank + 1) / comm.nranks;
+        } else {
+            lo = 0;
+            hi = rows;
+        }
     }
     void account_hess(const Half &h, uint64_t iters) {
         const size_t s = sizeof(T);
@@ -938,18 +966,33 @@ struct Problem final : CtxBase {
         const size_t o = h.soff() * kp;
         const uint64_t Ds = h.s1 - h.s0, len = Ds * kp;
         const T *fq = h.freq ? h.freq + h.soff() : nullptr;
+        T reg = T(prm.lambda);   // regulariser still to be added to Hv by cg_step
+        int slotted = 0;         // V.Hv arrives as sc->vpart[it] partial sums
+        const bool partial = h.sliced;  // vHv / r2 are sums over this rank's part only
         if (h.side && h.X->diagonal && diag_fast && (!comm.active() || h.sliced)) {
             // row-local Hessian: direction update, Hv, regulariser and V.Hv in one pass
             side_diag_iter<T>(h.Yown->view(), h.X->view(), h.Q1, V.p, R.p, Hv.p, h.freq, T(prm.lambda),
                               T(prm.omega), T(h.n1), kp, it, sc, st);
+            reg = T(0);
+        } else if (fused_dot) {
+            // 3 kernels per cross iteration: [direction + V QTQ], [Hessian rows + V.Hv], [step]
+            if (h.side) {
+                uint64_t lo, hi;
+                share_of(h, lo, hi);
+                cg_dir<T>(V.p + o, R.p + o, Hv.p + o, len, it, sc, fq, T(prm.lambda), kp, lo, hi, 1, st);
+            }
+            hess_scatter(h, Gate{sc, it}, it);
+            slotted = 1;
+            comm.allreduce(sc->vpart[it], size_t(kDotSlots), st);   // every rank holds a share
         } else {
-            cg_dir<T>(V.p + o, R.p + o, Hv.p + o, len, it, sc, st);
+            cg_dir<T>(V.p + o, R.p + o, Hv.p + o, len, it, sc, fq, T(0), kp, 0, 0, 0, st);
             hess_scatter(h, Gate{sc, it});
             cg_reg_dot<T>(Hv.p + o, V.p + o, fq, T(prm.lambda), Ds, kp, it, sc, 1, st);
+            reg = T(0);
         }
-        if (h.sliced) comm.allreduce(&sc->vHv[it], 1, st);          // slice partial -> global V.Hv
-        cg_step<T>(S.p + o, R.p + o, V.p + o, Hv.p + o, len, it, sc, st);
-        if (h.sliced) comm.allreduce(&sc->r2[it + 1], 1, st);
+        if (partial && !slotted) comm.allreduce(&sc->vHv[it], 1, st);   // slice partial -> global V.Hv
+        cg_step<T>(S.p + o, R.p + o, V.p + o, Hv.p + o, len, it, sc, fq, reg, kp, slotted, st);
+        if (partial) comm.allreduce(&sc->r2[it + 1], 1, st);
         OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaEventRecord(cg_ev[it], st));
     }

@@ -216,6 +216,20 @@ __device__ __forceinline__ double block_sum(double v) {
     return v;
 }
 
+// block-wide fp64 sum added to *out by one thread (the order of the blocks is not fixed)
+__device__ __forceinline__ void block_add(double local, double *out) {
+    local = block_sum(local);
+    if (threadIdx.x == 0 && local != 0.0) atomicAdd(out, local);
+}
+
+// warp-wide fp64 sum added to one of `slots` partial sums (no block barrier: the row kernels'
+// warps finish at very different times)
+__device__ __forceinline__ void warp_add_slot(double local, double *part, unsigned slots) {
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local != 0.0)
+        atomicAdd(part + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (slots - 1)), local);
+}
+
 inline int ceil_div(size_t a, size_t b) { return int((a + b - 1) / b); }
 
 }  // namespace ocffm

@@ -108,13 +108,31 @@ void launch_gram(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb
 // ---------------------------------------------------------------------------------------------
 // Row GEMM: C[M x KP] = A[M x Ka] * B[Ka x KP], B tiny (Ka <= a few hundred), A streamed once.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int KP, int TM, int TN>
+// DIR: A is the CG direction V [M x KP] (lda == Ka == KP) and the tile load also performs the
+// direction update of iteration gate.it (V = R + beta V, ffm.cpp:808-810), clears Hv and adds
+// this block's share of lambda sum_f c_f |V_f|^2 to *dir.vv -- cg_dir folded into the pass that
+// reads V anyway.
+template <typename T>
+struct DirFuse {
+    T *V;                 // same memory as A
+    const T *R;
+    T *Hv;
+    const T *freq;        // per row of A, or nullptr
+    T lambda;
+    uint64_t sum_lo, sum_hi;   // rows whose |V|^2 this rank accounts for
+    double *vv;
+};
+
+template <typename T, int KP, int TM, int TN, bool DIR>
 __global__ void __launch_bounds__(kThreads)
 k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restrict__ B,
-          T *__restrict__ C, uint64_t M, Gate gate) {
+          T *__restrict__ C, uint64_t M, Gate gate, DirFuse<T> dir) {
     pdl_enter();
     constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
     if (!gate_open(gate)) return;
+    T beta = T(0);
+    double vv_local = 0;
+    if (DIR && gate.it > 0) beta = T(gate.sc->r2[gate.it] / gate.sc->r2[gate.it - 1]);
     constexpr int BK = sizeof(T) == 8 ? 16 : 32;   // keeps static shared memory under 48 KB
     __shared__ __align__(16) T As[BK][BM + 4];
     __shared__ __align__(16) T Bs[BK][KP];
@@ -129,7 +147,26 @@ k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restric
         for (int e = tid; e < BM * (BK / 4); e += kThreads) {
             const int r = e / (BK / 4), c = (e % (BK / 4)) * 4;
             V4<T> v = zero4<T>();
-            if (m0 + r < M && k0 + c < Ka) v = ldg4(A + (m0 + r) * lda + k0 + c);
+            if (m0 + r < M && k0 + c < Ka) {
+                if (DIR) {
+                    const size_t off = (m0 + r) * lda + k0 + c;
+                    v = ld4(dir.V + off);
+                    if (gate.it > 0) {
+                        const V4<T> rr = ld4(dir.R + off);
+                        v.x = rr.x + beta * v.x; v.y = rr.y + beta * v.y;
+                        v.z = rr.z + beta * v.z; v.w = rr.w + beta * v.w;
+                        st4(dir.V + off, v);
+                    }
+                    st4(dir.Hv + off, zero4<T>());
+                    if (m0 + r >= dir.sum_lo && m0 + r < dir.sum_hi) {
+                        const T cf = dir.freq ? dir.lambda * dir.freq[m0 + r] : dir.lambda;
+                        vv_local += double(cf) * (double(v.x) * v.x + double(v.y) * v.y + double(v.z) * v.z +
+                                                  double(v.w) * v.w);
+                    }
+                } else {
+                    v = ldg4(A + (m0 + r) * lda + k0 + c);
+                }
+            }
             As[c + 0][r] = v.x;
             As[c + 1][r] = v.y;
             As[c + 2][r] = v.z;
@@ -167,14 +204,19 @@ k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restric
             }
         }
     }
+    if (DIR) block_add(vv_local, dir.vv + (blockIdx.x & (kDotSlots - 1)));
 }
 
 template <typename T, int KP, int TM, int TN>
 void launch_rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, Gate gate,
-                    cudaStream_t s) {
+                    const DirFuse<T> *dir, cudaStream_t s) {
     constexpr int NN = KP / TN, NM = kThreads / NN, BM = NM * TM;
-    OC_LAUNCH((k_rowgemm<T, KP, TM, TN>), unsigned((M + BM - 1) / BM), kThreads, 0, s, A, lda, Ka, B,
-              C, M, gate);
+    if (dir)
+        OC_LAUNCH((k_rowgemm<T, KP, TM, TN, true>), unsigned((M + BM - 1) / BM), kThreads, 0, s, A, lda, Ka,
+                  B, C, M, gate, *dir);
+    else
+        OC_LAUNCH((k_rowgemm<T, KP, TM, TN, false>), unsigned((M + BM - 1) / BM), kThreads, 0, s, A, lda, Ka,
+                  B, C, M, gate, DirFuse<T>{});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,20 +314,30 @@ k_cg_init(T *__restrict__ G, const T *__restrict__ W, const T *__restrict__ freq
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_dir(T *__restrict__ V, const T *__restrict__ R, T *__restrict__ Hv, uint64_t nvec, int it,
-         const SolveScalars *sc) {
+         const SolveScalars *sc, const T *__restrict__ freq, T lambda, int kp4, uint64_t sum_lo,
+         uint64_t sum_hi, double *vv_out) {
     pdl_enter();
     if (!gate_open(Gate{sc, it})) return;
     const T beta = it > 0 ? T(sc->r2[it] / sc->r2[it - 1]) : T(0);
+    double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
-        if (it > 0) {
-            const V4<T> r = ld4(R + i * 4);
+        if (it > 0 || vv_out) {
             V4<T> v = ld4(V + i * 4);
-            v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
-            st4(V + i * 4, v);
+            if (it > 0) {
+                const V4<T> r = ld4(R + i * 4);
+                v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
+                st4(V + i * 4, v);
+            }
+            if (vv_out && i >= sum_lo && i < sum_hi) {
+                const T c = freq ? lambda * freq[i / kp4] : lambda;
+                local += double(c) * (double(v.x) * v.x + double(v.y) * v.y + double(v.z) * v.z + double(v.w) * v.w);
+            }
         }
         st4(Hv + i * 4, zero4<T>());
     }
+    // lambda sum_f c_f |V_f|^2, the regulariser's share of V.Hv
+    if (vv_out) block_add(local, vv_out + (blockIdx.x & (kDotSlots - 1)));
 }
 
 template <typename T>
@@ -310,14 +362,28 @@ k_cg_reg_dot(T *__restrict__ Hv, const T *__restrict__ V, const T *__restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T *__restrict__ Hv,
-          uint64_t nvec, int it, SolveScalars *sc) {
+          uint64_t nvec, int it, SolveScalars *sc, const T *__restrict__ freq, T lambda, int kp4,
+          int slotted) {
     pdl_enter();
     if (!gate_open(Gate{sc, it})) return;
-    const T alpha = T(sc->r2[it] / sc->vHv[it]);
+    double vhv = sc->vHv[it];
+    if (slotted) {   // fused iteration: V.Hv arrives as kDotSlots partial sums (blockDim == kDotSlots)
+        __shared__ double tot;
+        const double s = block_sum(sc->vpart[it][threadIdx.x]);
+        if (threadIdx.x == 0) tot = s;
+        __syncthreads();
+        vhv = tot;
+    }
+    const T alpha = T(sc->r2[it] / vhv);
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += uint64_t(gridDim.x) * blockDim.x) {
-        const V4<T> v = ld4(V + i * 4), h = ld4(Hv + i * 4);
+        const V4<T> v = ld4(V + i * 4);
+        V4<T> h = ld4(Hv + i * 4);
+        if (lambda != T(0)) {   // Hv holds the data term only: add lambda c_f V here (ffm.cpp:788-790)
+            const T c = freq ? lambda * freq[i / kp4] : lambda;
+            h.x += c * v.x; h.y += c * v.y; h.z += c * v.z; h.w += c * v.w;
+        }
         V4<T> sv = ld4(S + i * 4), r = ld4(R + i * 4);
         sv.x += alpha * v.x; sv.y += alpha * v.y; sv.z += alpha * v.z; sv.w += alpha * v.w;
         r.x -= alpha * h.x; r.y -= alpha * h.y; r.z -= alpha * h.z; r.w -= alpha * h.w;
@@ -433,18 +499,29 @@ void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb,
 }
 
 template <typename T>
-void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp, Gate gate,
-             cudaStream_t s) {
+static void rowgemm_impl(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp,
+                         Gate gate, const DirFuse<T> *dir, cudaStream_t s) {
     if (!M) return;
     switch (kp) {
-        case 4: launch_rowgemm<T, 4, 1, 4>(A, lda, Ka, B, C, M, gate, s); break;
-        case 8: launch_rowgemm<T, 8, 1, 4>(A, lda, Ka, B, C, M, gate, s); break;
-        case 16: launch_rowgemm<T, 16, 2, 4>(A, lda, Ka, B, C, M, gate, s); break;
-        case 32: launch_rowgemm<T, 32, 4, 4>(A, lda, Ka, B, C, M, gate, s); break;
-        case 64: launch_rowgemm<T, 64, 4, 8>(A, lda, Ka, B, C, M, gate, s); break;
-        case 128: launch_rowgemm<T, 128, 4, 8>(A, lda, Ka, B, C, M, gate, s); break;
+        case 4: launch_rowgemm<T, 4, 1, 4>(A, lda, Ka, B, C, M, gate, dir, s); break;
+        case 8: launch_rowgemm<T, 8, 1, 4>(A, lda, Ka, B, C, M, gate, dir, s); break;
+        case 16: launch_rowgemm<T, 16, 2, 4>(A, lda, Ka, B, C, M, gate, dir, s); break;
+        case 32: launch_rowgemm<T, 32, 4, 4>(A, lda, Ka, B, C, M, gate, dir, s); break;
+        case 64: launch_rowgemm<T, 64, 4, 8>(A, lda, Ka, B, C, M, gate, dir, s); break;
+        case 128: launch_rowgemm<T, 128, 4, 8>(A, lda, Ka, B, C, M, gate, dir, s); break;
         default: throw Error(-6, "padded latent dimension must be 4..128");
     }
+}
+template <typename T>
+void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp, Gate gate,
+             cudaStream_t s) {
+    rowgemm_impl<T>(A, lda, Ka, B, C, M, kp, gate, nullptr, s);
+}
+template <typename T>
+void rowgemm_dir(T *V, const T *R, T *Hv, const T *freq, T lambda, uint64_t sum_lo, uint64_t sum_hi,
+                 const T *B, T *C, uint64_t M, int kp, int it, SolveScalars *sc, cudaStream_t s) {
+    const DirFuse<T> dir{V, R, Hv, freq, lambda, sum_lo, sum_hi, sc->vpart[it]};
+    rowgemm_impl<T>(V, uint32_t(kp), uint32_t(kp), B, C, M, kp, Gate{sc, it}, &dir, s);
 }
 
 template <typename T>
@@ -475,9 +552,11 @@ void cg_init(T *G, const T *W, const T *freq, T lambda, T *R, T *V, T *S, uint64
 }
 
 template <typename T>
-void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, const SolveScalars *sc, cudaStream_t s) {
+void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, SolveScalars *sc, const T *freq, T lambda, int kp,
+            uint64_t sum_lo, uint64_t sum_hi, int vv, cudaStream_t s) {
     if (!n) return;
-    OC_LAUNCH((k_cg_dir<T>), ew_blocks(n / 4), kThreads, 0, s, V, R, Hv, n / 4, it, sc);
+    OC_LAUNCH((k_cg_dir<T>), ew_blocks(n / 4), kThreads, 0, s, V, R, Hv, n / 4, it, sc, freq, lambda, kp / 4,
+              sum_lo * (kp / 4), sum_hi * (kp / 4), vv ? sc->vpart[it] : nullptr);
 }
 
 template <typename T>
@@ -490,10 +569,12 @@ void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, 
 }
 
 template <typename T>
-void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc,
-             cudaStream_t s) {
+void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc, const T *freq,
+             T lambda, int kp, int slotted, cudaStream_t s) {
     if (!n) return;
-    OC_LAUNCH((k_cg_step<T>), ew_blocks(n / 4), kThreads, 0, s, S, R, V, Hv, n / 4, it, sc);
+    static_assert(kThreads == kDotSlots, "k_cg_step sums one vpart slot per thread");
+    OC_LAUNCH((k_cg_step<T>), ew_blocks(n / 4), kThreads, 0, s, S, R, V, Hv, n / 4, it, sc, freq, lambda,
+              kp / 4, slotted);
 }
 
 template <typename T>
@@ -560,11 +641,14 @@ void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStr
     template void unpad_to_f64<T>(const T *, uint32_t, double *, uint64_t, uint32_t, cudaStream_t); \
     template void cg_init<T>(T *, const T *, const T *, T, T *, T *, T *, uint64_t, int,            \
                              SolveScalars *, cudaStream_t);                                         \
-    template void cg_dir<T>(T *, const T *, T *, uint64_t, int, const SolveScalars *, cudaStream_t); \
+    template void cg_dir<T>(T *, const T *, T *, uint64_t, int, SolveScalars *, const T *, T, int,  \
+                            uint64_t, uint64_t, int, cudaStream_t);                                 \
+    template void rowgemm_dir<T>(T *, const T *, T *, const T *, T, uint64_t, uint64_t, const T *,  \
+                                 T *, uint64_t, int, int, SolveScalars *, cudaStream_t);            \
     template void cg_reg_dot<T>(T *, const T *, const T *, T, uint64_t, int, int, SolveScalars *,   \
                                 int, cudaStream_t);                                                 \
     template void cg_step<T>(T *, T *, const T *, const T *, uint64_t, int, SolveScalars *,         \
-                             cudaStream_t);                                                         \
+                             const T *, T, int, int, cudaStream_t);                                 \
     template void axpy<T>(T *, const T *, T, uint64_t, cudaStream_t);                               \
     template void reduce_sum<T>(const T *, uint64_t, int, double *, cudaStream_t);                  \
     template void col_sums<T>(const T *, uint32_t, uint32_t, uint32_t, uint32_t, double *,          \

@@ -21,6 +21,9 @@ struct CsrView {
     // fold_hot() adds the replicas back.  Null when the field has no hot feature.
     const int16_t *hot_slot; // [D] or nullptr
     T *shadow;               // [n_hot * kHotReplicas * kp]
+    // one feature per row (rowptr[i] == i) / that feature is i itself: the row kernels skip the
+    // dependent rowptr -> idx loads (id fields; two fewer round trips per work item)
+    bool diagonal, identity;
 };
 constexpr int kHotReplicas = 64;
 
@@ -46,7 +49,12 @@ struct SolveScalars {       // device-resident fp64 scalars of one CG solve (ffm
     double misc[8];
     double partials[148 * 8];   // per-block partial sums of the deterministic reductions
     unsigned counter[4];
+    // V.Hv of iteration it when the Hessian pass accumulates it on the way (fused CG iteration):
+    // the sum of these kDotSlots partial sums, spread so that the per-warp REDs do not serialise
+    // on one address.  cg_step adds them up (every block, same order).
+    double vpart[24][256];
 };
+constexpr int kDotSlots = 256;
 
 // Device-side gate of the speculatively enqueued CG iteration `it` (ffm.cpp:780: the loop runs
 // while g2 * cg_eps < r2): every kernel of an iteration returns at once when the stop test
@@ -82,7 +90,8 @@ void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, ui
 // hs_cross row pass (ffm.cpp:715-738): phi = X_i V, tau = X_i (V QTQ), ka = sum_j (phi.q_j) q_j
 template <typename T>
 void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
-                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, cudaStream_t s);
+                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out,
+                     cudaStream_t s);   // dot_out (optional) += V . Hv, as sum over work items of phi . z
 
 // ysum[row] = sum of y-tilde over the row (first half of gd_side's z_i, ffm.cpp:577-580)
 template <typename T>
@@ -92,7 +101,7 @@ void ytilde_rowsum(const OmegaView<T> &Y, T *ysum, int kp, cudaStream_t s);
 template <typename T>
 void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, const T *a1,
                const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
-               int kp, Gate gate, cudaStream_t s);
+               int kp, Gate gate, double *dot_out, cudaStream_t s);
 
 // Same-side CG iteration on a DIAGONAL field (every row has exactly one feature and the features
 // form a permutation, e.g. a user-id / item-id field): hs_side (ffm.cpp:603-624) is then local to
@@ -150,16 +159,24 @@ template <typename T>
 void cg_init(T *G, const T *W, const T *freq, T lambda, T *R, T *V, T *S, uint64_t D, int kp,
              SolveScalars *sc, cudaStream_t s);
 // it > 0: V = R + (r2[it]/r2[it-1]) V ; always Hv = 0
+// vv != 0: also sc->vHv[it] += lambda sum_f c_f |V_f|^2 over rows [sum_lo, sum_hi) (the regulariser's
+// share of V.Hv when the Hessian pass accumulates the data share itself)
 template <typename T>
-void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, const SolveScalars *sc, cudaStream_t s);
+void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, SolveScalars *sc, const T *freq, T lambda, int kp,
+            uint64_t sum_lo, uint64_t sum_hi, int vv, cudaStream_t s);
+// cross halves: the same direction update folded into VQ = V * QTQ (one pass over V)
+template <typename T>
+void rowgemm_dir(T *V, const T *R, T *Hv, const T *freq, T lambda, uint64_t sum_lo, uint64_t sum_hi,
+                 const T *B, T *C, uint64_t M, int kp, int it, SolveScalars *sc, cudaStream_t s);
 // Hv += lambda * (freq ? freq[row] : 1) * V ; sc->vHv[it] += V . Hv
 template <typename T>
 void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, int it,
                 SolveScalars *sc, int gated, cudaStream_t s);
-// alpha = r2[it]/vHv[it] ; S += alpha V ; R -= alpha Hv ; sc->r2[it+1] += ||R||^2
+// alpha = r2[it]/vHv[it] ; S += alpha V ; R -= alpha (Hv + lambda c_f V) ; sc->r2[it+1] += ||R||^2
+// (lambda = 0 when Hv already contains the regulariser)
 template <typename T>
-void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc,
-             cudaStream_t s);
+void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc, const T *freq,
+             T lambda, int kp, int slotted, cudaStream_t s);   // slotted: V.Hv = sum(sc->vpart[it])
 template <typename T>
 void axpy(T *y, const T *x, T alpha, uint64_t n, cudaStream_t s);
 // dst[i] = src[pos[i]]: refreshes one orientation of the y-tilde cache from the other

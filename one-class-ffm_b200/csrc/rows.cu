@@ -149,64 +149,69 @@ k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
         pk.z += w * (t1.z + zi * o.z + b.z);
         pk.w += w * (t1.w + zi * o.w + b.w);
     }
-    const uint32_t e = X.rowptr[row + 1];
-    for (uint32_t t = X.rowptr[row]; t < e; ++t)
-        red4(scatter_row(X, Gout, X.idx[t], kp) + lg * 4, scale4(pk, X.val[t]));
+    const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
+    for (uint32_t t = xb; t < xe; ++t)
+        red4(scatter_row(X, Gout, X.identity ? row : X.idx[t], kp) + lg * 4, scale4(pk, X.val[t]));
 }
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
-             const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate) {
+             const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate,
+             double *__restrict__ dot_out) {
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
     constexpr int U = G < 8 ? G : 8;   // gathers kept in flight per lane
     if (!gate_open(gate)) return;
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
-    if (item >= Y.n_items) return;
-    const uint32_t lg = threadIdx.x % G;
-    const uint32_t mask = group_mask<G>();
-    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
-    const uint32_t cnt = c & 0x7fffffffu;
-    const bool first = (c >> 31) != 0;
-    const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
-    uint32_t j = lg < cnt ? Y.idx[beg + lg] : 0u;
-    V4<T> phi = zero4<T>(), tau = zero4<T>();
-    for (uint32_t t = xb; t < xe; ++t) {
-        const size_t off = size_t(X.idx[t]) * kp + lg * 4;
-        const T v = X.val[t];
-        fma4(phi, v, ldg4(V + off));
-        if (first) fma4(tau, v, ldg4(VQ + off));
-    }
-    V4<T> ka = zero4<T>();
-    const T *qbase = Q1 + lg * 4;
-    for (uint32_t base = 0; base < cnt; base += G) {
-        const uint32_t nb = base + G + lg;
-        const uint32_t jn = nb < cnt ? Y.idx[beg + nb] : 0u;   // next batch of column ids
-        const uint32_t rem = cnt - base;
-        if (rem >= uint32_t(G)) {
-#pragma unroll
-            for (int l0 = 0; l0 < G; l0 += U) {
-                V4<T> q[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
-#pragma unroll
-                for (int u = 0; u < U; ++u) fma4(ka, gsum<G>(dot4(phi, q[u]), mask), q[u]);
-            }
-        } else {
-            for (uint32_t l = 0; l < rem; ++l) {
-                const V4<T> q = ldg4(qbase + size_t(__shfl_sync(mask, j, l, G)) * ldq);
-                fma4(ka, gsum<G>(dot4(phi, q), mask), q);
-            }
+    T vhv = T(0);   // this lane's share of V . (X^T z) = (X_i V) . z
+    if (item < Y.n_items) {
+        const uint32_t lg = threadIdx.x % G;
+        const uint32_t mask = group_mask<G>();
+        const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
+        const uint32_t cnt = c & 0x7fffffffu;
+        const bool first = (c >> 31) != 0;
+        const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
+        uint32_t j = lg < cnt ? Y.idx[beg + lg] : 0u;
+        V4<T> phi = zero4<T>(), tau = zero4<T>();
+        for (uint32_t t = xb; t < xe; ++t) {
+            const size_t off = size_t(X.identity ? row : X.idx[t]) * kp + lg * 4;
+            const T v = X.val[t];
+            fma4(phi, v, ldg4(V + off));
+            if (first) fma4(tau, v, ldg4(VQ + off));
         }
-        j = jn;
+        V4<T> ka = zero4<T>();
+        const T *qbase = Q1 + lg * 4;
+        for (uint32_t base = 0; base < cnt; base += G) {
+            const uint32_t nb = base + G + lg;
+            const uint32_t jn = nb < cnt ? Y.idx[beg + nb] : 0u;   // next batch of column ids
+            const uint32_t rem = cnt - base;
+            if (rem >= uint32_t(G)) {
+#pragma unroll
+                for (int l0 = 0; l0 < G; l0 += U) {
+                    V4<T> q[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) fma4(ka, gsum<G>(dot4(phi, q[u]), mask), q[u]);
+                }
+            } else {
+                for (uint32_t l = 0; l < rem; ++l) {
+                    const V4<T> q = ldg4(qbase + size_t(__shfl_sync(mask, j, l, G)) * ldq);
+                    fma4(ka, gsum<G>(dot4(phi, q), mask), q);
+                }
+            }
+            j = jn;
+        }
+        const T omw = T(1) - w;
+        V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
+                   omw * ka.w + w * tau.w};
+        vhv = dot4(phi, z);
+        for (uint32_t t = xb; t < xe; ++t)
+            red4(scatter_row(X, Hv, X.identity ? row : X.idx[t], kp) + lg * 4, scale4(z, X.val[t]));
     }
-    const T omw = T(1) - w;
-    V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
-               omw * ka.w + w * tau.w};
-    for (uint32_t t = xb; t < xe; ++t)
-        red4(scatter_row(X, Hv, X.idx[t], kp) + lg * 4, scale4(z, X.val[t]));
+    if (dot_out) warp_add_slot(double(vhv), dot_out, kDotSlots);
 }
 
 template <typename T, int G>
@@ -273,32 +278,38 @@ template <typename T, int G, int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_side_rows(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, const T *__restrict__ a1,
             const T *__restrict__ sa1, const T *__restrict__ ysum, const double *__restrict__ bsum,
-            const T *__restrict__ V, T w, T r, T n1, T *__restrict__ Out, Gate gate) {
+            const T *__restrict__ V, T w, T r, T n1, T *__restrict__ Out, Gate gate,
+            double *__restrict__ dot_out) {
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
     if (!gate_open(gate)) return;
     const uint64_t g = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
-    if (g >= uint64_t(X.row1 - X.row0)) return;
-    const uint32_t lg = threadIdx.x % G;
-    const uint32_t mask = group_mask<G>();
-    const uint32_t row = X.row0 + uint32_t(g);
-    const T cnt = T(Y.rowptr[row + 1] - Y.rowptr[row]);
-    const V4<T> q = ldg4(Q1 + size_t(row) * kp + lg * 4);
-    const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
-    T z;
-    if (MODE == 0) {
-        // z_i = w (n1 (a_i - r) + sum(b) + sa_i) + sum_Omega_i ((1-w) ytilde - w (1-r))
-        z = w * (n1 * (a1[row] - r) + T(*bsum) + sa1[row]) + (T(1) - w) * ysum[row] -
-            w * (T(1) - r) * cnt;
-    } else {
-        // d_i (q_i . X_i V),  d_i = (1-w) |Omega_i| + w n1
-        T acc = T(0);
+    T vhv = T(0);
+    if (g < uint64_t(X.row1 - X.row0)) {
+        const uint32_t lg = threadIdx.x % G;
+        const uint32_t mask = group_mask<G>();
+        const uint32_t row = X.row0 + uint32_t(g);
+        const T cnt = T(Y.rowptr[row + 1] - Y.rowptr[row]);
+        const V4<T> q = ldg4(Q1 + size_t(row) * kp + lg * 4);
+        const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
+        T z;
+        if (MODE == 0) {
+            // z_i = w (n1 (a_i - r) + sum(b) + sa_i) + sum_Omega_i ((1-w) ytilde - w (1-r))
+            z = w * (n1 * (a1[row] - r) + T(*bsum) + sa1[row]) + (T(1) - w) * ysum[row] -
+                w * (T(1) - r) * cnt;
+        } else {
+            // d_i (q_i . X_i V),  d_i = (1-w) |Omega_i| + w n1
+            T acc = T(0);
+            for (uint32_t t = xb; t < xe; ++t)
+                acc += X.val[t] * dot4(q, ldg4(V + size_t(X.idx[t]) * kp + lg * 4));
+            const T sdot = gsum<G>(acc, mask);
+            z = sdot * ((T(1) - w) * cnt + w * n1);
+            if (lg == 0) vhv = sdot * z;   // V . X^T (q z) = (q . X_i V) z, once per row
+        }
         for (uint32_t t = xb; t < xe; ++t)
-            acc += X.val[t] * dot4(q, ldg4(V + size_t(X.idx[t]) * kp + lg * 4));
-        z = gsum<G>(acc, mask) * ((T(1) - w) * cnt + w * n1);
+            red4(scatter_row(X, Out, X.idx[t], kp) + lg * 4, scale4(q, X.val[t] * z));
     }
-    for (uint32_t t = xb; t < xe; ++t)
-        red4(scatter_row(X, Out, X.idx[t], kp) + lg * 4, scale4(q, X.val[t] * z));
+    if (MODE == 1 && dot_out) warp_add_slot(double(vhv), dot_out, kDotSlots);
 }
 
 // block-wide fp64 sum + deterministic last-block combine (same scheme as dense.cu's finish_sum)
@@ -477,10 +488,11 @@ void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, ui
 
 template <typename T>
 void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
-                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, cudaStream_t s) {
+                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out,
+                     cudaStream_t s) {
     if (!Y.n_items) return;
     OC_DISPATCH_G(kp, OC_LAUNCH((k_hess_cross<T, G>), blocks_for(Y.n_items, G), kThreads, 0, s, Y, X,
-                                Q1, ldq, V, VQ, w, Hv, gate));
+                                Q1, ldq, V, VQ, w, Hv, gate, dot_out));
 }
 
 template <typename T>
@@ -493,15 +505,15 @@ void ytilde_rowsum(const OmegaView<T> &Y, T *ysum, int kp, cudaStream_t s) {
 template <typename T>
 void side_rows(int mode, const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, const T *a1,
                const T *sa1, const T *ysum, const double *bsum, const T *V, T w, T r, T n1, T *Out,
-               int kp, Gate gate, cudaStream_t s) {
+               int kp, Gate gate, double *dot_out, cudaStream_t s) {
     const uint64_t rows = X.row1 - X.row0;
     if (!rows) return;
     if (mode == 0) {
         OC_DISPATCH_G(kp, OC_LAUNCH((k_side_rows<T, G, 0>), blocks_for(rows, G), kThreads, 0, s, Y, X,
-                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out, gate));
+                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out, gate, dot_out));
     } else {
         OC_DISPATCH_G(kp, OC_LAUNCH((k_side_rows<T, G, 1>), blocks_for(rows, G), kThreads, 0, s, Y, X,
-                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out, gate));
+                                    Q1, a1, sa1, ysum, bsum, V, w, r, n1, Out, gate, dot_out));
     }
 }
 
@@ -566,11 +578,12 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
                                      const T *, const T *, const T *, const T *, T, T, T *, int,   \
                                      cudaStream_t);                                                \
     template void hess_cross_rows<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, \
-                                     const T *, const T *, T, T *, int, Gate, cudaStream_t);       \
+                                     const T *, const T *, T, T *, int, Gate, double *,            \
+                                     cudaStream_t);                                                \
     template void ytilde_rowsum<T>(const OmegaView<T> &, T *, int, cudaStream_t);                  \
     template void side_rows<T>(int, const OmegaView<T> &, const CsrView<T> &, const T *, const T *, \
                                const T *, const T *, const double *, const T *, T, T, T, T *, int, \
-                               Gate, cudaStream_t);                                                \
+                               Gate, double *, cudaStream_t);                                      \
     template void sddmm_add<T>(const OmegaView<T> &, const T *, uint32_t, const T *, uint32_t, int, \
                                cudaStream_t);                                                      \
     template void ytilde_base<T>(const OmegaView<T> &, const T *, const T *, cudaStream_t);        \
