@@ -1,5 +1,5 @@
-"""Rows sharded over 2 GPUs (NCCL all-reduce of Grams / gradients / Hessian-vector products,
-all-gather of updated embeddings) must reproduce the single-GPU solve."""
+"""Rows sharded over 2 GPUs (all-reduce of Grams / gradients / Hessian-vector products / CG scalars
+over peer memory or NCCL, all-gather of updated embeddings) must reproduce the single-GPU solve."""
 import os
 import subprocess
 import sys
@@ -15,22 +15,25 @@ pytestmark = pytest.mark.gpu
 WORKER = os.path.join(ROOT, "tests", "multi_gpu_worker.py")
 
 
-def run(world, out, dtype):
+def run(world, out, dtype, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", WORKER, out, dtype]
     if world == 1:
         cmd = [sys.executable, WORKER, out, dtype]
-    subprocess.run(cmd, check=True, timeout=600, capture_output=True)
+    subprocess.run(cmd, check=True, timeout=600, capture_output=True, env=dict(os.environ, **(env or {})))
     return np.load(out)
 
 
+@pytest.mark.parametrize("peer", ["1", "0"])   # small all-reduces over peer memory (peer.cu) / all on NCCL
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_two_ranks_match_one(dtype):
+def test_two_ranks_match_one(dtype, peer):
     if ocffm.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if peer == "0" and dtype == "f32":
+        pytest.skip("covered by the fp64 case")
     with tempfile.TemporaryDirectory() as tmp:
         one = run(1, os.path.join(tmp, "one.npz"), dtype)
-        two = run(2, os.path.join(tmp, "two.npz"), dtype)
+        two = run(2, os.path.join(tmp, "two.npz"), dtype, {"OCFFM_PEER": peer})
     tol = 1e-9 if dtype == "f64" else 2e-3
     if dtype == "f64":
         assert list(one["cgs"]) == list(two["cgs"])
