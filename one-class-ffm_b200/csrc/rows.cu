@@ -100,6 +100,26 @@ k_spmm_update(CsrView<T> X, const T *__restrict__ S, T *__restrict__ XS, T *__re
     }
 }
 
+// G == 8: the partial dot products d[0..7] a lane holds for 8 gathered rows -> lane l returns the
+// full sum of d[l] (butterfly reduce-scatter: 4 + 2 + 1 = 7 shuffles instead of 8 x 3)
+template <typename T>
+__device__ __forceinline__ T reduce_scatter8(const T (&d)[8], uint32_t lg, uint32_t mask) {
+    const bool b2 = (lg & 4u) != 0, b1 = (lg & 2u) != 0, b0 = (lg & 1u) != 0;
+    T e[4], f[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T send = b2 ? d[i] : d[i + 4], keep = b2 ? d[i + 4] : d[i];
+        e[i] = keep + __shfl_xor_sync(mask, send, 4, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T send = b1 ? e[i] : e[i + 2], keep = b1 ? e[i + 2] : e[i];
+        f[i] = keep + __shfl_xor_sync(mask, send, 2, 8);
+    }
+    const T send = b0 ? f[0] : f[1], keep = b0 ? f[1] : f[0];
+    return keep + __shfl_xor_sync(mask, send, 1, 8);
+}
+
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
@@ -193,8 +213,17 @@ k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
 #pragma unroll
                     for (int u = 0; u < U; ++u)
                         q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+                    if constexpr (G == 8 && sizeof(T) == 4) {   // fp64 would spill: it keeps the plain sums
+                        T d[8];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) fma4(ka, gsum<G>(dot4(phi, q[u]), mask), q[u]);
+                        for (int u = 0; u < 8; ++u) d[u] = dot4(phi, q[u]);
+                        const T mine = reduce_scatter8(d, lg, mask);   // phi . q of gathered row lg
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) fma4(ka, __shfl_sync(mask, mine, u, 8), q[u]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) fma4(ka, gsum<G>(dot4(phi, q[u]), mask), q[u]);
+                    }
                 }
             } else {
                 for (uint32_t l = 0; l < rem; ++l) {
@@ -242,10 +271,17 @@ k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *_
 #pragma unroll
                 for (int x = 0; x < U; ++x)
                     q[x] = ldg4(vbase + size_t(__shfl_sync(mask, j, l0 + x, G)) * ldv);
+                if constexpr (G == 8) {
+                    T d[8];
 #pragma unroll
-                for (int x = 0; x < U; ++x) {
-                    const T s = gsum<G>(dot4(u, q[x]), mask);
-                    if (int(lg) == l0 + x) mine = s;
+                    for (int x = 0; x < 8; ++x) d[x] = dot4(u, q[x]);
+                    mine = reduce_scatter8(d, lg, mask);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < U; ++x) {
+                        const T s = gsum<G>(dot4(u, q[x]), mask);
+                        if (int(lg) == l0 + x) mine = s;
+                    }
                 }
             }
         } else {
