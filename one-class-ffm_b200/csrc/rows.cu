@@ -144,20 +144,18 @@ k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
         const uint32_t t = beg + base + lg;
         const uint32_t j = ok ? Y.idx[t] : 0u;
         const T sc = ok ? omw * Y.yt[t] - cst : T(0);
-        const uint32_t rem = cnt - base;
-        if (rem >= uint32_t(G)) {
+        // Short rows take the same U-wide batches as full ones: entries past cnt gather row 0 with
+        // a zero coefficient, so every gather of a batch is in flight at once (a one-at-a-time
+        // tail would pay one L2 round trip per entry, and most item rows are all tail).
 #pragma unroll
-            for (int l0 = 0; l0 < G; l0 += U) {
-                V4<T> q[U];
+        for (int l0 = 0; l0 < G; l0 += U) {
+            if (base + l0 >= cnt) break;
+            V4<T> q[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+            for (int u = 0; u < U; ++u)
+                q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
 #pragma unroll
-                for (int u = 0; u < U; ++u) fma4(pk, __shfl_sync(mask, sc, l0 + u, G), q[u]);
-            }
-        } else {
-            for (uint32_t l = 0; l < rem; ++l)
-                fma4(pk, __shfl_sync(mask, sc, l, G), ldg4(qbase + size_t(__shfl_sync(mask, j, l, G)) * ldq));
+            for (int u = 0; u < U; ++u) fma4(pk, __shfl_sync(mask, sc, l0 + u, G), q[u]);
         }
     }
     if (first) {
@@ -205,30 +203,28 @@ k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
         for (uint32_t base = 0; base < cnt; base += G) {
             const uint32_t nb = base + G + lg;
             const uint32_t jn = nb < cnt ? Y.idx[beg + nb] : 0u;   // next batch of column ids
-            const uint32_t rem = cnt - base;
-            if (rem >= uint32_t(G)) {
 #pragma unroll
-                for (int l0 = 0; l0 < G; l0 += U) {
-                    V4<T> q[U];
+            for (int l0 = 0; l0 < G; l0 += U) {
+                if (base + l0 >= cnt) break;   // entries past cnt: row 0, zero coefficient (see k_grad_cross)
+                V4<T> q[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
-                    if constexpr (G == 8 && sizeof(T) == 4) {   // fp64 would spill: it keeps the plain sums
-                        T d[8];
+                for (int u = 0; u < U; ++u)
+                    q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+                if constexpr (G == 8 && sizeof(T) == 4) {   // fp64 would spill: it keeps the plain sums
+                    T d[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) d[u] = dot4(phi, q[u]);
-                        const T mine = reduce_scatter8(d, lg, mask);   // phi . q of gathered row lg
+                    for (int u = 0; u < 8; ++u) d[u] = dot4(phi, q[u]);
+                    T mine = reduce_scatter8(d, lg, mask);   // phi . q of gathered row lg
+                    if (base + lg >= cnt) mine = T(0);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) fma4(ka, __shfl_sync(mask, mine, u, 8), q[u]);
-                    } else {
+                    for (int u = 0; u < 8; ++u) fma4(ka, __shfl_sync(mask, mine, u, 8), q[u]);
+                } else {
 #pragma unroll
-                        for (int u = 0; u < U; ++u) fma4(ka, gsum<G>(dot4(phi, q[u]), mask), q[u]);
+                    for (int u = 0; u < U; ++u) {
+                        T sdot = gsum<G>(dot4(phi, q[u]), mask);
+                        if (base + l0 + u >= cnt) sdot = T(0);
+                        fma4(ka, sdot, q[u]);
                     }
-                }
-            } else {
-                for (uint32_t l = 0; l < rem; ++l) {
-                    const V4<T> q = ldg4(qbase + size_t(__shfl_sync(mask, j, l, G)) * ldq);
-                    fma4(ka, gsum<G>(dot4(phi, q), mask), q);
                 }
             }
             j = jn;
@@ -262,32 +258,25 @@ k_sddmm_add(OmegaView<T> Y, const T *__restrict__ Uown, uint32_t ldu, const T *_
         const bool ok = base + lg < cnt;
         const uint32_t t = beg + base + lg;
         const uint32_t j = ok ? Y.idx[t] : 0u;
-        const uint32_t rem = cnt - base;
         T mine = T(0);
-        if (rem >= uint32_t(G)) {
 #pragma unroll
-            for (int l0 = 0; l0 < G; l0 += U) {
-                V4<T> q[U];
+        for (int l0 = 0; l0 < G; l0 += U) {
+            if (base + l0 >= cnt) break;   // entries past cnt gather row 0 and are not stored
+            V4<T> q[U];
 #pragma unroll
-                for (int x = 0; x < U; ++x)
-                    q[x] = ldg4(vbase + size_t(__shfl_sync(mask, j, l0 + x, G)) * ldv);
-                if constexpr (G == 8) {
-                    T d[8];
+            for (int x = 0; x < U; ++x)
+                q[x] = ldg4(vbase + size_t(__shfl_sync(mask, j, l0 + x, G)) * ldv);
+            if constexpr (G == 8) {
+                T d[8];
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) d[x] = dot4(u, q[x]);
-                    mine = reduce_scatter8(d, lg, mask);
-                } else {
+                for (int x = 0; x < 8; ++x) d[x] = dot4(u, q[x]);
+                mine = reduce_scatter8(d, lg, mask);
+            } else {
 #pragma unroll
-                    for (int x = 0; x < U; ++x) {
-                        const T s = gsum<G>(dot4(u, q[x]), mask);
-                        if (int(lg) == l0 + x) mine = s;
-                    }
+                for (int x = 0; x < U; ++x) {
+                    const T s = gsum<G>(dot4(u, q[x]), mask);
+                    if (int(lg) == l0 + x) mine = s;
                 }
-            }
-        } else {
-            for (uint32_t l = 0; l < rem; ++l) {
-                const T s = gsum<G>(dot4(u, ldg4(vbase + size_t(__shfl_sync(mask, j, l, G)) * ldv)), mask);
-                if (lg == l) mine = s;
             }
         }
         if (ok) Y.yt[t] += mine;
