@@ -101,8 +101,13 @@ struct Comm {
     unsigned long long seq = 0;
     uint64_t peer_calls = 0, nccl_calls = 0;
 
-    ~Comm() {
+    void close_peers() {
         for (void *p : opened) cudaIpcCloseMemHandle(p);
+        opened.clear();
+        peer_ok = false;
+    }
+    ~Comm() {
+        close_peers();
         if (pv.base[rank]) cudaFree(pv.base[rank]);
         if (peer_err_host) cudaFreeHost(peer_err_host);
         if (comm) Nccl::get().CommDestroy(comm);
@@ -171,6 +176,55 @@ struct Comm {
         OC_CUDA(cudaMemcpyAsync(&total, agree.p, sizeof(float), cudaMemcpyDeviceToHost, s));
         OC_CUDA(cudaStreamSynchronize(s));
         peer_ok = total == float(nranks);
+    }
+    // Collective: maps the same cudaMalloc'ed buffer of every rank into this process.  Returns false
+    // (on every rank alike) when any rank could not export or import a handle.
+    bool share(void *mine, void **out, cudaStream_t s) {
+        if (!peer_ok) return false;
+        struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+        Msg m{};
+        m.ok = cudaIpcGetMemHandle(&m.h, mine) == cudaSuccess;
+        cudaGetLastError();
+        DevBuf<unsigned char> x;
+        x.alloc(sizeof(Msg) * nranks);
+        OC_CUDA(cudaMemcpyAsync(x.p + sizeof(Msg) * rank, &m, sizeof(Msg), cudaMemcpyHostToDevice, s));
+        Nccl &n = Nccl::get();
+        OC_NCCL(n.GroupStart());
+        for (int q = 0; q < nranks; ++q)
+            OC_NCCL(n.Broadcast(x.p + sizeof(Msg) * q, x.p + sizeof(Msg) * q, sizeof(Msg), ncclChar, q, comm, s));
+        OC_NCCL(n.GroupEnd());
+        std::vector<Msg> all(nranks);
+        OC_CUDA(cudaMemcpyAsync(all.data(), x.p, sizeof(Msg) * nranks, cudaMemcpyDeviceToHost, s));
+        OC_CUDA(cudaStreamSynchronize(s));
+        bool ok = true;
+        for (int q = 0; q < nranks; ++q) ok = ok && all[q].ok;
+        for (int q = 0; q < nranks && ok; ++q) {
+            out[q] = mine;
+            if (q == rank) continue;
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = false;
+                cudaGetLastError();
+            } else {
+                opened.push_back(p);
+                out[q] = p;
+            }
+        }
+        DevBuf<float> agree;
+        agree.alloc(1);
+        const float v = ok ? 1.0f : 0.0f;
+        OC_CUDA(cudaMemcpyAsync(agree.p, &v, sizeof(float), cudaMemcpyHostToDevice, s));
+        OC_NCCL(n.AllReduce(agree.p, agree.p, 1, ncclFloat, ncclSum, comm, s));
+        float total = 0;
+        OC_CUDA(cudaMemcpyAsync(&total, agree.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+        OC_CUDA(cudaStreamSynchronize(s));
+        return total == float(nranks);
+    }
+    unsigned long long gather_seq = 0;
+    template <typename T>
+    void peer_gather_rows(const PeerBuffers &pb, uint64_t rows, uint32_t ld, cudaStream_t s) {
+        const uint64_t lo = rows * rank / nranks, hi = rows * (rank + 1) / nranks;
+        peer_allgather_rows<T>(pv, pb, lo, hi, ld, ++gather_seq, s);
     }
     void check_peer() {
         if (peer_ok && *static_cast<volatile int *>(peer_err_host))
@@ -261,6 +315,11 @@ struct Problem final : CtxBase {
     // copy right before it is next read (4 bytes gathered per entry instead of a d-wide row).
     // OCFFM_MIRROR_YT=0 updates both copies as the reference does; multi-rank runs always do
     // (each rank owns different slices of the two orientations).
+    // multi-rank: the CG step S of every rank mapped here, so a sliced half publishes its part of
+    // the step by direct NVLink stores (peer.cu) instead of an NCCL all-gather; OCFFM_PEER_GATHER=0
+    bool peer_gather = false, peer_gather_allowed = true;
+    PeerBuffers S_peers{};
+    void *S_shared = nullptr;
     bool mirror_yt = false, mirror_allowed = true;
     // OCFFM_FUSED_DOT=0: separate direction / regulariser+dot kernels per CG iteration (5 instead of 3)
     bool fused_dot = true;
@@ -372,6 +431,7 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_CHUNK")) chunk = std::max(1, atoi(e));
         if (const char *e = getenv("OCFFM_EVAL_TC")) eval_tc = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_MIRROR_YT")) mirror_allowed = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_PEER_GATHER")) peer_gather_allowed = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_FUSED_DOT")) fused_dot = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
@@ -389,6 +449,8 @@ struct Problem final : CtxBase {
     }
     ~Problem() override {
         cudaSetDevice(device);
+        if (st) cudaStreamSynchronize(st);
+        comm.close_peers();   // imports first, then this rank's own buffers are freed
         for (auto &e : hv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto &e : cg_ev) cudaEventDestroy(e);
         cudaEventDestroy(g2_ev);
@@ -731,6 +793,17 @@ struct Problem final : CtxBase {
         for (auto &F : XV) OC_REQUIRE(F.set, "an item field is missing");
         for (auto &bk : blocks)
             if (bk.exists) OC_REQUIRE(bk.has_w && bk.has_h, "a parameter block was never set");
+        if (comm.active() && comm.peer_ok && peer_gather_allowed && slice_cg) {
+            // the CG step at its final size, shared once (collective: every rank is in init_state)
+            uint64_t maxD = 0;
+            for (auto &F : XU) maxD = std::max(maxD, F.D);
+            for (auto &F : XV) maxD = std::max(maxD, F.D);
+            S.ensure(maxD * kp);
+            if (S_shared != S.p) {
+                peer_gather = comm.share(S.p, S_peers.buf, st);
+                S_shared = S.p;
+            }
+        }
         // init_pair, ffm.cpp:346-349
         for (auto &bk : blocks) {
             if (!bk.exists) continue;
@@ -1034,7 +1107,10 @@ struct Problem final : CtxBase {
         const uint64_t len = h.D * kp, nnzY = h.Yown->nnz, nnzX = h.X->nnz;
         // sliced half: one all-gather of the step per half solve, then every rank applies the whole
         // step to its replicas (W, P, a) with the single-rank kernels
-        if (h.sliced) comm.allgather_rows(S.p, h.D, kp, st);
+        if (h.sliced) {
+            if (peer_gather) comm.template peer_gather_rows<T>(S_peers, h.D, kp, st);
+            else comm.allgather_rows(S.p, h.D, kp, st);
+        }
         axpy<T>(h.W1, S.p, T(1), len, st);
         const T *q_side = h.side ? h.Q1 : nullptr;
         if (!comm.active() || h.sliced) {

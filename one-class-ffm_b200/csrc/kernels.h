@@ -245,7 +245,20 @@ struct PeerView {
     size_t cap;                           // largest message in bytes; a [slot][src] region is 2*cap
     int *error;                           // local flag: set when a wait timed out
 };
-inline size_t peer_area_bytes(int nranks, size_t cap) { return size_t(2) * nranks * cap * 2; }
+// area layout: [2 slots][nranks] line regions of 2*cap bytes, then the barrier block
+// (kPeerMaxRanks arrival flags + one block counter)
+inline size_t peer_barrier_offset(int nranks, size_t cap) { return size_t(2) * nranks * cap * 2; }
+inline size_t peer_area_bytes(int nranks, size_t cap) { return peer_barrier_offset(nranks, cap) + 1024; }
+// The same [rows x ld] buffer of every rank, mapped here (buf[rank] is local).
+struct PeerBuffers {
+    void *buf[kPeerMaxRanks];
+};
+// All-gather of row slices by direct stores: this rank's rows [row_lo, row_hi) go to the same
+// offset of every peer's buffer, then the ranks meet at a flag barrier inside the same kernel, so
+// the next kernel of every stream sees the whole matrix.  seq: 1, 2, 3, ... per call.
+template <typename T>
+void peer_allgather_rows(const PeerView &pv, const PeerBuffers &pb, uint64_t row_lo, uint64_t row_hi,
+                         uint32_t ld, unsigned long long seq, cudaStream_t s);
 // buf[0:n] <- sum over ranks, in rank order, identical bits everywhere; seq: 1, 2, 3, ... per call
 template <typename T>
 void peer_allreduce(const PeerView &pv, T *buf, size_t n, unsigned long long seq, cudaStream_t s);

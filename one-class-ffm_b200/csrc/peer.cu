@@ -11,6 +11,8 @@
 // flag round trip, and the result is bit-identical on all ranks (the device-side CG gate relies
 // on that).  Two slots are enough: a peer can only be one call ahead, because call seq+1 cannot
 // complete anywhere before this rank has contributed to it.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -106,7 +108,65 @@ k_peer_allreduce(PeerView pv, T *__restrict__ buf, uint32_t n, uint32_t n_lines,
     }
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Own rows -> every peer's copy (16-byte stores over NVLink), then a barrier: the last block of
+// this rank to finish publishes seq in every peer's arrival flags and waits for theirs.
+__global__ void __launch_bounds__(kPeerThreads)
+k_peer_allgather(PeerView pv, PeerBuffers pb, size_t byte_off, size_t n16, size_t barrier_off,
+                 unsigned long long seq) {
+    pdl_enter();
+    const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<unsigned char *>(pb.buf[pv.rank]) + byte_off);
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += size_t(gridDim.x) * blockDim.x) {
+        const uint4 v = src[i];
+        for (int q = 0; q < pv.nranks; ++q)
+            if (q != pv.rank)
+                reinterpret_cast<uint4 *>(static_cast<unsigned char *>(pb.buf[q]) + byte_off)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    unsigned long long *flags = reinterpret_cast<unsigned long long *>(pv.base[pv.rank] + barrier_off);
+    unsigned *counter = reinterpret_cast<unsigned *>(flags + kPeerMaxRanks);
+    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && int(threadIdx.x) < pv.nranks && int(threadIdx.x) != pv.rank) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long *>(pv.base[threadIdx.x] + barrier_off) + pv.rank, seq);
+        const unsigned long long t0 = global_ns();
+        for (uint32_t spin = 1; ld_acquire_sys(flags + threadIdx.x) != seq; ++spin) {
+            if ((spin & 0x3ffu) == 0 && global_ns() - t0 > kPeerTimeoutNs) {
+                atomicExch(pv.error, 1);
+                break;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+template <typename T>
+void peer_allgather_rows(const PeerView &pv, const PeerBuffers &pb, uint64_t row_lo, uint64_t row_hi,
+                         uint32_t ld, unsigned long long seq, cudaStream_t s) {
+    const size_t byte_off = size_t(row_lo) * ld * sizeof(T), bytes = size_t(row_hi - row_lo) * ld * sizeof(T);
+    OC_REQUIRE(byte_off % 16 == 0 && bytes % 16 == 0, "peer_allgather_rows: rows must be 16-byte multiples");
+    const size_t n16 = bytes / 16;
+    unsigned blocks = unsigned(std::min<size_t>((n16 + kPeerThreads - 1) / kPeerThreads, size_t(kSMs) * 4));
+    if (blocks == 0) blocks = 1;
+    OC_LAUNCH(k_peer_allgather, blocks, kPeerThreads, 0, s, pv, pb, byte_off, n16,
+              peer_barrier_offset(pv.nranks, pv.cap), seq);
+}
+template void peer_allgather_rows<float>(const PeerView &, const PeerBuffers &, uint64_t, uint64_t, uint32_t,
+                                         unsigned long long, cudaStream_t);
+template void peer_allgather_rows<double>(const PeerView &, const PeerBuffers &, uint64_t, uint64_t, uint32_t,
+                                          unsigned long long, cudaStream_t);
 
 template <typename T>
 void peer_allreduce(const PeerView &pv, T *buf, size_t n, unsigned long long seq, cudaStream_t s) {
