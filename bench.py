@@ -36,9 +36,10 @@ WORKLOADS = {
     "C1": ("C1", 16, 2_000),
     "C3": ("C3", 16, 20_000),
     "C4": ("C4", 32, 20_000),
+    "C5": ("C2", 64, 30_000),   # BASELINE configs[4]: d=64 KKBox-shaped scoring + top-k sweep (see "eval")
 }
-SHAPE_M = {"C1": 10_000, "C2": 30_000, "C3": 8_000_000, "C4": 4_000_000}
-CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02}
+SHAPE_M = {"C1": 10_000, "C2": 30_000, "C3": 8_000_000, "C4": 4_000_000, "C5": 30_000}
+CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02, "C5": 0.1}
 
 
 def peaks():
@@ -167,7 +168,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     shape, k, test_rows = WORKLOADS[args.workload]
-    config = dict(workload=f"{args.workload}: KKBox-shaped synthetic one-class set" if args.workload == "C2"
+    config = dict(workload=f"{args.workload}: KKBox-shaped synthetic one-class set" if shape == "C2"
                   else f"{args.workload} synthetic one-class set",
                   shape=shape, k=k, lam=HYPER["lam"], omega=HYPER["omega"], r=HYPER["r"],
                   self_side=not args.ns, seed=args.seed, zipf=1.3, l2="inputs larger than L2 (126 MB)")
