@@ -238,7 +238,7 @@ void eval_metrics(const uint32_t *ids, const uint32_t *cold_ids80, const uint8_t
 constexpr int kPeerMaxRanks = 16;
 constexpr int kPeerMaxBlocks = 64;
 constexpr int kPeerThreads = 256;
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+constexpr unsigned long long kPeerTimeoutNs = 120ull * 1000 * 1000 * 1000;   // host-side skew between ranks can be seconds
 struct PeerView {
     unsigned char *base[kPeerMaxRanks];   // every rank's staging area, mapped here (base[rank] is local)
     int nranks, rank;
