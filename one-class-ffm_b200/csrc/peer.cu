@@ -141,7 +141,8 @@ k_peer_allgather(PeerView pv, PeerBuffers pb, size_t byte_off, size_t n16, size_
         __threadfence_system();
         st_release_sys(reinterpret_cast<unsigned long long *>(pv.base[threadIdx.x] + barrier_off) + pv.rank, seq);
         const unsigned long long t0 = global_ns();
-        for (uint32_t spin = 1; ld_acquire_sys(flags + threadIdx.x) != seq; ++spin) {
+        // arrival flags only grow, so ">= seq" also holds if a peer were ever a call ahead
+        for (uint32_t spin = 1; ld_acquire_sys(flags + threadIdx.x) < seq; ++spin) {
             if ((spin & 0x3ffu) == 0 && global_ns() - t0 > kPeerTimeoutNs) {
                 atomicExch(pv.error, 1);
                 break;
