@@ -96,6 +96,52 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(self.reasons), samples=len(self.samples))
 
 
+def run_port_arm(args, shape, k, test_rows):
+    """oracle/_ref was not built (no /root/reference on this machine): times the plain-C restatement
+    of the same path (oracle/liboracle.so, one thread) on a smaller sample.  kind = "port"."""
+    import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import pyoracle
+    except Exception:
+        return None
+    scale = (args.cpu_scale or CPU_SAMPLE_SCALE[args.workload]) * 0.25
+    ds = synth.generate(shape, seed=args.seed, scale=scale, test_rows=max(64, int(test_rows * scale * 0.1)))
+    o = pyoracle.Oracle(ds, k=k, **HYPER)
+    o.init_model_rng()
+    o.init_state()
+    nnz_y = int(ds.train.idx.size)
+    fu = ds.users.f
+    nnzx = [int(f.idx.size) for f in ds.users.fields] + [int(f.idx.size) for f in ds.items.fields]
+    n_trav, sec, cgs = 0.0, 0.0, []
+    t_all = time.time()
+    for e in range(args.warmup + args.steps):
+        timed = e >= args.warmup
+        before_epoch = o.cg_iters_total()
+        t0 = time.time()
+        order = sorted(o.blocks(), key=lambda b: (2 if b[0] < fu <= b[1] else (0 if b[1] < fu else 1), b))
+        for f1, f2 in order:               # one_epoch order: user side, item side, cross (ffm.cpp:852-870)
+            before = o.cg_iters_total()
+            o.solve_block(f1, f2)
+            c = o.cg_iters_total() - before
+            if timed:
+                xa, xb, cross = nnzx[f1], nnzx[f2], f1 < fu <= f2
+                n_trav += 2 * nnz_y + xa + xb + c * ((nnz_y if cross else 0) + (xa + xb) / 2.0) \
+                    + 2 * (2 * nnz_y) + xa + xb
+        if timed:
+            sec += time.time() - t0
+            cgs.append(o.cg_iters_total() - before_epoch)
+    t0 = time.time()
+    o.validate(want_topk=False)
+    t_val = time.time() - t0
+    sample = (f"{shape} scaled x{scale} (m={ds.m}, n={ds.n}, nnz_y={nnz_y}), k={k}, {args.steps} timed epochs "
+              f"after {args.warmup} warm-up, plain-C port of the reference path, 1 thread")
+    return dict(kind="port", value=n_trav / sec, sec_per_epoch=sec / max(1, args.steps), cores=1,
+                host_cores=os.cpu_count() or 1, sample=sample, cg_iters=cgs, wall_s=time.time() - t_all,
+                eval_users_per_s=ds.test.rows / t_val if ds.test is not None and t_val > 0 else None,
+                harness="liboracle.so")
+
+
 def run_reference_arm(args, shape, k, test_rows):
     """Times the unmodified reference (oracle/_ref) on host cores on a bounded sample."""
     import synth
@@ -104,7 +150,7 @@ def run_reference_arm(args, shape, k, test_rows):
     if not os.path.exists(harness):
         harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(harness):
-        return None
+        return run_port_arm(args, shape, k, test_rows)
     scale = args.cpu_scale or CPU_SAMPLE_SCALE[args.workload]
     ds = synth.generate(shape, seed=args.seed, scale=scale, test_rows=max(64, int(test_rows * scale * 0.1)))
     ncpu = os.cpu_count() or 1
