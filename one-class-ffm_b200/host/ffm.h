@@ -92,6 +92,10 @@ public:
 
     void init();
     void solve();
+    // Next point of a (lambda, omega) grid on the data already resident on the device
+    // (script/grid.sh runs one process per point; each starts rand() from its default seed, so
+    // does this): fresh random model, new hyper-parameters, caches rebuilt.  Needs init() first.
+    void restart(ImpDouble new_lambda, ImpDouble new_omega);
     ImpDouble func();
 
     void write_header(std::ofstream &o_f) const;

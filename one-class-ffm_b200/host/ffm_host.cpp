@@ -499,6 +499,17 @@ void ImpProblem::init() {
     check(ocffm_init_state(ctx), "ocffm_init_state");
 }
 
+void ImpProblem::restart(ImpDouble new_lambda, ImpDouble new_omega) {
+    if (!ctx) throw runtime_error("ImpProblem::restart() needs init() first");
+    param->lambda = lambda = new_lambda;
+    param->omega = w = new_omega;
+    srand(1);   // the state rand() has at the start of a process (ISO C), i.e. of a separate run
+    init_model_random();
+    check(ocffm_set_hyper(ctx, lambda, w, r), "ocffm_set_hyper");
+    push_model();
+    check(ocffm_init_state(ctx), "ocffm_init_state");
+}
+
 void ImpProblem::one_epoch() {
     check(ocffm_one_epoch(ctx), "ocffm_one_epoch");
     host_model_stale = true;

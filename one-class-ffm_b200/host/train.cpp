@@ -7,12 +7,18 @@
 // Flags of the reference: -l -k -t -w -r -c -p -o --ns --freq (parsing stops at the first token
 // that is not a flag, numeric flags only need one digit somewhere in their value, exactly like
 // is_numerical there).  Added: --f64 (fp64 on the device), --device N, --load <binary model>,
-// --save-binary <path>, --predict-only (evaluate a loaded model once, no training).
+// --save-binary <path>, --predict-only (evaluate a loaded model once, no training), --cache, and
+// --grid-l / --grid-w: a (lambda, omega) grid like script/grid.sh:186-240 solved point after point
+// on the data uploaded once; every point prints "config -l <l> -w <w>" and then exactly the log a
+// separate run with those flags prints; -o / --save-binary paths get ".l<l>.w<w>" appended.
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <sstream>
 #include <stdexcept>
+#include <vector>
+#include <algorithm>
 
 #include "ffm.h"
 #ifdef _OPENMP
@@ -27,7 +33,30 @@ struct Option {
     shared_ptr<Parameter> param = make_shared<Parameter>();
     string item_path, train_path, test_path, model_path, load_path, binary_path;
     bool predict_only = false, cache = false;
+    vector<double> grid_l, grid_w;
 };
+
+// "1,4,16" -> {1, 4, 16}; every item needs a digit, like the other numeric flags
+vector<double> number_list(const string &text, const string &flag) {
+    vector<double> out;
+    size_t pos = 0;
+    while (pos <= text.size()) {
+        const size_t end = min(text.find(',', pos), text.size());
+        const string item = text.substr(pos, end - pos);
+        bool digit = false;
+        for (char c : item) digit = digit || isdigit(static_cast<unsigned char>(c));
+        if (!digit) throw invalid_argument(flag + " should be followed by a comma-separated list of numbers");
+        out.push_back(atof(item.c_str()));
+        pos = end + 1;
+    }
+    return out;
+}
+
+string number_tag(double v) {
+    ostringstream os;
+    os << v;
+    return os.str();
+}
 
 bool has_digit(const char *s) {
     for (; *s; ++s)
@@ -54,7 +83,8 @@ const char *kUsage =
     "--load <path>: start from a binary model (save_binary_model layout)\n"
     "--save-binary <path>: also write the binary model\n"
     "--predict-only: evaluate the loaded model on the test set and exit\n"
-    "--cache: keep / reuse <file>.ocffm.bin binary caches of the parsed text files\n";
+    "--cache: keep / reuse <file>.ocffm.bin binary caches of the parsed text files\n"
+    "--grid-l <l1,l2,..> / --grid-w <w1,w2,..>: solve every (lambda, omega) pair on the data uploaded once\n";
 
 // value of a numeric flag; `miss` is thrown when the value is absent, `bad` when it has no digit
 const char *numeric_value(int argc, char **argv, int &i, const char *miss, const char *bad) {
@@ -82,6 +112,9 @@ Option parse_option(int argc, char **argv) {
             if (i == argc - 1) throw invalid_argument("need to specify path after " + a);
             const string v = argv[++i];
             (a == "-p" ? opt.test_path : a == "-o" ? opt.model_path : a == "--load" ? opt.load_path : opt.binary_path) = v;
+        } else if (a == "--grid-l" || a == "--grid-w") {
+            if (i == argc - 1) throw invalid_argument("need to specify a list after " + a);
+            (a == "--grid-l" ? opt.grid_l : opt.grid_w) = number_list(argv[++i], a);
         } else if (a == "--ns") p.self_side = false;
         else if (a == "--freq") p.freq = true;
         else if (a == "--f64") p.dtype = OCFFM_F64;
@@ -127,9 +160,35 @@ int main(int argc, char *argv[]) {
         }
         if (!Ut->file_name.empty()) load(Ut, true, U->Ds.data(), "te");
 
+        const bool grid = !opt.grid_l.empty() || !opt.grid_w.empty();
+        if (grid && (opt.predict_only || !opt.load_path.empty()))
+            throw invalid_argument("--grid-l / --grid-w start every point from a fresh random model: "
+                                   "not with --load or --predict-only");
+        if (opt.grid_l.empty()) opt.grid_l.push_back(opt.param->lambda);
+        if (opt.grid_w.empty()) opt.grid_w.push_back(opt.param->omega);
+        if (grid) {
+            opt.param->lambda = opt.grid_l[0];
+            opt.param->omega = opt.grid_w[0];
+        }
+
         ImpProblem prob(U, Ut, V, opt.param);
         if (!opt.load_path.empty()) prob.load_binary_model(opt.load_path);
         prob.init();
+        if (grid) {
+            bool first = true;
+            for (double l : opt.grid_l)
+                for (double w : opt.grid_w) {
+                    if (!first) prob.restart(l, w);
+                    first = false;
+                    cout << "config -l " << number_tag(l) << " -w " << number_tag(w) << endl;
+                    prob.solve();
+                    const string tag = ".l" + number_tag(l) + ".w" + number_tag(w);
+                    string text_path = opt.model_path + tag, binary_path = opt.binary_path + tag;
+                    if (!opt.model_path.empty()) save_model(prob, text_path);
+                    if (!opt.binary_path.empty()) prob.save_binary_model(binary_path);
+                }
+            return 0;
+        }
         if (opt.predict_only) {
             if (Ut->file_name.empty()) throw invalid_argument("--predict-only needs -p <test set>");
             prob.init_va(5);

@@ -62,6 +62,14 @@ def test_cli_usage_and_argument_errors():
     assert r.returncode == 1 and "need to specify path after -p" in r.stderr
     r = run(["-k", "8", "--ns"])
     assert r.returncode == 1 and "training data not specified" in r.stderr
+    # grid runner flags
+    r = run(["--grid-l", "1,x", "a", "b"])
+    assert r.returncode == 1 and "--grid-l should be followed by a comma-separated list of numbers" in r.stderr
+    r = run(["--grid-w"])
+    assert r.returncode == 1 and "need to specify a list after --grid-w" in r.stderr
+    base = os.path.join(GOLDEN, "tiny", "tiny")
+    r = run(["--grid-l", "1,4", "--predict-only", base + ".item", base + ".tr"])
+    assert r.returncode == 1 and "not with --load or --predict-only" in r.stderr
 
 
 def test_cli_fails_loudly_without_gpu():

@@ -67,3 +67,49 @@ def test_train_matches_reference_cli(case, mode):
     num = max(np.max(np.abs(got_rows[k] - want_rows[k])) for k in want_rows)
     den = max(np.max(np.abs(v)) for v in want_rows.values())
     assert num <= tol * den, (num, den)
+
+
+def test_grid_runner_matches_separate_runs():
+    """--grid-l / --grid-w solve every (lambda, omega) point on the data uploaded once; each point
+    must print exactly the log of a separate run with those flags (fp64: byte for byte) and write
+    the same model."""
+    gdir = os.path.join(GOLDEN, "tiny")
+    flags = open(os.path.join(gdir, "cli_flags.txt")).read().split()
+    base = os.path.join(gdir, "tiny")
+
+    def strip(flag, argv):   # drop "-l v" / "-w v" from the golden flags
+        out, skip = [], False
+        for a in argv:
+            if skip:
+                skip = False
+            elif a == flag:
+                skip = True
+            else:
+                out.append(a)
+        return out
+    common = strip("-w", strip("-l", flags)) + ["--f64", "-c", "1", "-p", base + ".te"]
+    data = [base + ".item", base + ".tr"]
+    ls, ws = ["4", "0.5"], ["0.0078125", "0.0625"]
+    with tempfile.TemporaryDirectory() as tmp:
+        gm = os.path.join(tmp, "grid_model.txt")
+        g = subprocess.run([TRAIN] + common + ["--grid-l", ",".join(ls), "--grid-w", ",".join(ws), "-o", gm] + data,
+                           capture_output=True, text=True)
+        assert g.returncode == 0, g.stderr
+        sections = g.stdout.split("config ")[1:]
+        assert len(sections) == 4
+        i = 0
+        for l in ls:
+            for w in ws:
+                head, _, body = sections[i].partition("\n")
+                assert head == f"-l {l} -w {w}"
+                sm = os.path.join(tmp, f"single_{i}.txt")
+                one = subprocess.run([TRAIN] + common + ["-l", l, "-w", w, "-o", sm] + data,
+                                     capture_output=True, text=True)
+                assert one.returncode == 0, one.stderr
+                assert body == one.stdout, (l, w)
+                _, got = read_model(f"{gm}.l{l}.w{w}")
+                _, want = read_model(sm)
+                assert list(got) == list(want)
+                # 6 printed digits; fp64 atomics may reorder sums, so allow the last digit to move
+                assert all(np.allclose(got[k], want[k], rtol=1e-5, atol=1e-9) for k in want), (l, w)
+                i += 1
