@@ -96,6 +96,7 @@ struct Comm {
     // peer-memory path (peer.cu) for messages up to pv.cap bytes; NCCL carries the rest
     bool peer_ok = false;
     PeerView pv{};
+    unsigned char *area_owned = nullptr;   // this rank's staging area (pv.base[rank] when rank < kPeerMaxRanks)
     int *peer_err_host = nullptr;
     std::vector<void *> opened;
     unsigned long long seq = 0;
@@ -108,7 +109,7 @@ struct Comm {
     }
     ~Comm() {
         close_peers();
-        if (pv.base[rank]) cudaFree(pv.base[rank]);
+        if (area_owned) cudaFree(area_owned);
         if (peer_err_host) cudaFreeHost(peer_err_host);
         if (comm) Nccl::get().CommDestroy(comm);
     }
@@ -127,7 +128,8 @@ struct Comm {
         mine.ok = 1;
         unsigned char *area = nullptr;
         const size_t bytes = peer_area_bytes(nranks, cap);
-        if (cudaMalloc(&area, bytes) != cudaSuccess) mine.ok = 0;
+        if (cudaMalloc(&area, bytes) != cudaSuccess) { mine.ok = 0; area = nullptr; }
+        area_owned = area;
         if (mine.ok && cudaMemsetAsync(area, 0, bytes, s) != cudaSuccess) mine.ok = 0;
         if (mine.ok && cudaIpcGetMemHandle(&mine.h, area) != cudaSuccess) mine.ok = 0;
         if (mine.ok && cudaHostAlloc(&peer_err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) mine.ok = 0;
@@ -509,16 +511,20 @@ struct Problem final : CtxBase {
         F.rows = rows; F.D = D; F.nnz = nnz;
         std::vector<uint32_t> rp(rows + 1);
         for (uint64_t i = 0; i <= rows; ++i) rp[i] = uint32_t(rowptr[i]);
-        std::vector<T> v(nnz), fr(D, T(0));
+        // freq (ffm.cpp:235-241) is counted in integers like the reference's ImpLong: a float counter
+        // stops growing at 2^24 occurrences
+        std::vector<T> v(nnz), fr(D);
+        std::vector<uint64_t> occ(D, 0);
         for (uint64_t t = 0; t < nnz; ++t) {
             OC_REQUIRE(idx[t] < D, "feature index >= D");
             v[t] = T(val[t]);
-            fr[idx[t]] += T(1);   // freq, ffm.cpp:235-241
+            ++occ[idx[t]];
         }
+        for (uint64_t d = 0; d < D; ++d) fr[d] = T(occ[d]);
         F.diagonal = false;
         if (nnz == rows && D == rows && rows > 0) {
             bool ok = true;
-            for (uint64_t i = 0; i < rows && ok; ++i) ok = rowptr[i] == i && fr[idx[i]] == T(1);
+            for (uint64_t i = 0; i < rows && ok; ++i) ok = rowptr[i] == i && occ[idx[i]] == 1;
             F.diagonal = ok;
             bool id = ok;
             for (uint64_t i = 0; i < rows && id; ++i) id = idx[i] == i;
@@ -532,9 +538,9 @@ struct Problem final : CtxBase {
         // the most frequent first); they get kHotReplicas shadow rows each (kernels.h CsrView)
         F.n_hot = 0;
         if (side != OCFFM_SIDE_T && hot_min > 0) {
-            std::vector<std::pair<T, uint32_t>> cand;
+            std::vector<std::pair<uint64_t, uint32_t>> cand;
             for (uint64_t d = 0; d < D; ++d)
-                if (fr[d] >= T(hot_min)) cand.emplace_back(fr[d], uint32_t(d));
+                if (occ[d] >= hot_min) cand.emplace_back(occ[d], uint32_t(d));
             std::sort(cand.begin(), cand.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
             if (cand.size() > 1024) cand.resize(1024);
             if (!cand.empty()) {

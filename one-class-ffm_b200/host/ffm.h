@@ -13,11 +13,32 @@
 //   * load_binary_model() really loads (the reference's version opens an ofstream and
 //     truncates the file, ffm.cpp:1269-1301).
 #pragma once
+// The reference's header pulls these in for its users (ffm.h:1-31) and train.cpp relies on it
+// (shared_ptr, string, cout, stoi, invalid_argument, omp_set_num_threads ... unqualified), so the
+// mirror provides the same prelude, `using namespace std;` included.
+#include <algorithm>
+#include <cassert>
+#include <climits>
 #include <cstdint>
+#include <cstring>
 #include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
 #include <memory>
+#include <numeric>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <stdlib.h>
 #include <string>
+#include <unordered_set>
+#include <utility>
 #include <vector>
+
+#include <omp.h>
+
+using namespace std;
 
 #include "../../include/ocffm.h"
 
@@ -79,8 +100,11 @@ public:
     void transY(const std::vector<Node *> &YT);
     // additions: read() parses line ranges in parallel (OpenMP threads); a parsed
     // and split file can be cached in binary form and reloaded instead of re-parsing the text
-    void save_cache(const std::string &path) const;   // call after split_fields()
-    bool load_cache(const std::string &path);         // false: missing / stale / corrupt
+    // `filter`: the Ds vector the file was read with (read(has_label, ds)), i.e. the TRAINING set's Ds
+    // for a test file; it is recorded in the cache, and a cache written under another filter, or for
+    // a source file whose size or modification time changed since, is rejected.
+    void save_cache(const std::string &path, const std::vector<ImpLong> *filter = nullptr) const;   // after split_fields()
+    bool load_cache(const std::string &path, const std::vector<ImpLong> *filter = nullptr);         // false: missing / stale / corrupt
 };
 
 class ImpProblem {

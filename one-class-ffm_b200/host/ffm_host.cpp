@@ -5,6 +5,8 @@
 // with a single-pass buffer parser; the solver front-end only schedules C-ABI calls.
 #include "ffm.h"
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -246,9 +248,11 @@ void ImpData::read(bool has_label, const ImpLong *ds) {
 }
 
 // ---- binary cache of a parsed + split file --------------------------------------
-// Layout: magic "OCFFMBIN1", source size, then m n f nnz_x nnz_y, Ds, nnx, nny, per field
-// (rowptr, idx, val, freq), y_rowptr, y_idx, popular.  A cache is used only if the text file's
-// size matches what was recorded when it was written.
+// Layout: magic "OCFFMBIN2", source size, source mtime (ns), the Ds filter the file was read with
+// (empty for a training / item file; the training set's Ds for a test file, whose features
+// idx >= Ds[fid] were dropped and whose nnx depends on it, ffm.cpp:104-105), then m n f nnz_x nnz_y,
+// Ds, nnx, nny, per field (rowptr, idx, val, freq), y_rowptr, y_idx, popular.  A cache is used only
+// if the text file's size AND modification time are the recorded ones and the filter is the same.
 namespace {
 template <typename T>
 void put_vec(ofstream &o, const vector<T> &v) {
@@ -263,17 +267,23 @@ bool get_vec(ifstream &i, vector<T> &v) {
     v.resize(n);
     return n == 0 || bool(i.read(reinterpret_cast<char *>(v.data()), streamsize(n * sizeof(T))));
 }
-uint64_t file_size_of(const string &path) {
-    ifstream in(path, ios::binary | ios::ate);
-    return in ? uint64_t(in.tellg()) : 0;
+// {size, mtime in ns} of the source text file; {0, 0} when it cannot be stat'ed
+void file_stamp_of(const string &path, uint64_t out[2]) {
+    struct stat st;
+    out[0] = out[1] = 0;
+    if (stat(path.c_str(), &st) != 0) return;
+    out[0] = uint64_t(st.st_size);
+    out[1] = uint64_t(st.st_mtim.tv_sec) * 1000000000ull + uint64_t(st.st_mtim.tv_nsec);
 }
 }  // namespace
 
-void ImpData::save_cache(const string &path) const {
+void ImpData::save_cache(const string &path, const vector<ImpLong> *filter) const {
     ofstream o(path, ios::binary | ios::trunc);
-    o.write("OCFFMBIN1", 9);
-    const uint64_t src = file_size_of(file_name);
-    o.write(reinterpret_cast<const char *>(&src), sizeof src);
+    o.write("OCFFMBIN2", 9);
+    uint64_t stamp[2];
+    file_stamp_of(file_name, stamp);
+    o.write(reinterpret_cast<const char *>(stamp), sizeof stamp);
+    put_vec(o, filter ? *filter : vector<ImpLong>());
     const uint64_t hdr[5] = {m, n, f, nnz_x, nnz_y};
     o.write(reinterpret_cast<const char *>(hdr), sizeof hdr);
     put_vec(o, Ds); put_vec(o, nnx); put_vec(o, nny);
@@ -283,12 +293,16 @@ void ImpData::save_cache(const string &path) const {
     put_vec(o, y_rowptr); put_vec(o, y_idx); put_vec(o, popular);
 }
 
-bool ImpData::load_cache(const string &path) {
+bool ImpData::load_cache(const string &path, const vector<ImpLong> *filter) {
     ifstream i(path, ios::binary);
     char magic[9];
-    if (!i || !i.read(magic, 9) || memcmp(magic, "OCFFMBIN1", 9) != 0) return false;
-    uint64_t src = 0, hdr[5];
-    if (!i.read(reinterpret_cast<char *>(&src), sizeof src) || src != file_size_of(file_name)) return false;
+    if (!i || !i.read(magic, 9) || memcmp(magic, "OCFFMBIN2", 9) != 0) return false;
+    uint64_t stamp[2], now[2], hdr[5];
+    file_stamp_of(file_name, now);
+    if (!i.read(reinterpret_cast<char *>(stamp), sizeof stamp) || stamp[0] != now[0] || stamp[1] != now[1] || !now[0])
+        return false;
+    vector<ImpLong> recorded;
+    if (!get_vec(i, recorded) || recorded != (filter ? *filter : vector<ImpLong>())) return false;
     if (!i.read(reinterpret_cast<char *>(hdr), sizeof hdr)) return false;
     m = hdr[0]; n = hdr[1]; f = hdr[2]; nnz_x = hdr[3]; nnz_y = hdr[4];
     if (!get_vec(i, Ds) || !get_vec(i, nnx) || !get_vec(i, nny)) return false;
@@ -420,6 +434,12 @@ void ImpProblem::attach() {
     prm.self_side = param->self_side;
     prm.freq = param->freq;
     prm.dtype = param->dtype;
+    // An unmodified reference driver (train.cpp) has no flag for the device arithmetic: the
+    // environment can pick it (OCFFM_DTYPE=f64 reproduces the reference's log byte for byte).
+    if (const char *e = getenv("OCFFM_DTYPE")) {
+        if (!strcmp(e, "f64")) prm.dtype = OCFFM_F64;
+        else if (!strcmp(e, "f32")) prm.dtype = OCFFM_F32;
+    }
     prm.device = param->device;
     check(ocffm_create(&ctx, &prm, fu, fv, m, n), "ocffm_create");
     for (ImpInt fi = 0; fi < fu; fi++) {
@@ -635,6 +655,7 @@ void ImpProblem::load_binary_model(string &model_path) {
     };
     ImpInt mf, mfu, mfv, mk;
     get(&mf, sizeof mf); get(&mfu, sizeof mfu); get(&mfv, sizeof mfv); get(&mk, sizeof mk);
+    if (mf != mfu + mfv) throw invalid_argument("corrupt model file " + model_path + " (f != fu + fv)");
     if (mfu != U->f || mfv != V->f || mk != param->k)
         throw invalid_argument("model file does not match the data (fields or k differ)");
     fu = mfu; fv = mfv; f = mf; k = mk;
@@ -654,7 +675,11 @@ void ImpProblem::load_binary_model(string &model_path) {
             ImpInt fij;
             ImpLong wn, hn;
             get(&fij, sizeof fij); get(&wn, sizeof wn); get(&hn, sizeof hn);
-            if (fij != index_of(fi, fj) || wn != block_rows(fi) * k || hn != block_rows(fj) * k)
+            if (fij != index_of(fi, fj))   // the first stored block tells: (0,0) with same-side blocks, (0,fu) under --ns
+                throw invalid_argument(string("model file block layout mismatch: the file was written ") +
+                                       (param->self_side ? "with" : "without") + " --ns, this run is " +
+                                       (param->self_side ? "without" : "with") + " it");
+            if (wn != block_rows(fi) * k || hn != block_rows(fj) * k)
                 throw invalid_argument("model file block layout mismatch");
             W[fij].resize(wn);
             H[fij].resize(hn);

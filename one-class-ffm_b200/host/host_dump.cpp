@@ -44,6 +44,15 @@ static void dump(const string &pfx, ImpData &d, bool has_label) {
 }
 
 int main(int argc, char **argv) {
+    // host_dump --probe-cache <cache> <source text file> [d0,d1,...]: would load_cache accept it?
+    if (argc >= 4 && !strcmp(argv[1], "--probe-cache")) {
+        ImpData d(argv[3]);
+        vector<ImpLong> filter;
+        if (argc > 4)
+            for (char *tok = strtok(argv[4], ","); tok; tok = strtok(nullptr, ",")) filter.push_back(strtoul(tok, nullptr, 10));
+        puts(d.load_cache(argv[2], argc > 4 ? &filter : nullptr) ? "hit" : "miss");
+        return 0;
+    }
     if (argc < 6) {
         fprintf(stderr, "usage: host_dump <item> <train> <test|-> <out.ocfd> <k> [--ns]\n");
         return 2;
@@ -55,12 +64,12 @@ int main(int argc, char **argv) {
     string cache_dir;
     for (int i = 6; i + 1 < argc; i++)
         if (!strcmp(argv[i], "--via-cache")) cache_dir = argv[i + 1];
-    auto roundtrip = [&](shared_ptr<ImpData> &d, const char *tag) {
+    auto roundtrip = [&](shared_ptr<ImpData> &d, const char *tag, const vector<ImpLong> *filter = nullptr) {
         if (cache_dir.empty()) return;
         const string path = cache_dir + "/" + tag + ".bin";
-        d->save_cache(path);
+        d->save_cache(path, filter);
         shared_ptr<ImpData> fresh = make_shared<ImpData>(d->file_name);
-        if (!fresh->load_cache(path)) { fprintf(stderr, "cache reload failed for %s\n", tag); exit(3); }
+        if (!fresh->load_cache(path, filter)) { fprintf(stderr, "cache reload failed for %s\n", tag); exit(3); }
         d = fresh;
     };
     U->read(true);
@@ -73,7 +82,7 @@ int main(int argc, char **argv) {
     if (!Ut->file_name.empty()) {
         Ut->read(true, U->Ds.data());
         Ut->split_fields();
-        roundtrip(Ut, "T");
+        roundtrip(Ut, "T", &U->Ds);
     }
     g_out = fopen(argv[4], "wb");
     fputs("OCFD1\n", g_out);
@@ -100,5 +109,25 @@ int main(int argc, char **argv) {
             put("init." + to_string(f1) + "_" + to_string(f2) + ".H", prob.block_H(f1, f2));
         }
     fclose(g_out);
+    // optional "--binary-roundtrip <path>": save_binary_model (the reference's layout,
+    // ffm.cpp:1239-1267) -> load_binary_model into a FRESH problem; every block must come back
+    // bit for bit.  No device involved (the loader pushes to the device only when one is attached).
+    for (int i = 6; i + 1 < argc; i++)
+        if (!strcmp(argv[i], "--binary-roundtrip")) {
+            string path = argv[i + 1];
+            prob.save_binary_model(path);
+            ImpProblem fresh(U, Ut, V, prm);
+            fresh.prepare_shapes();
+            fresh.load_binary_model(path);
+            for (ImpInt f1 = 0; f1 < f; f1++)
+                for (ImpInt f2 = f1; f2 < f; f2++) {
+                    if (!prm->self_side && !(f1 < fu && f2 >= fu)) continue;
+                    if (fresh.block_W(f1, f2) != prob.block_W(f1, f2) || fresh.block_H(f1, f2) != prob.block_H(f1, f2)) {
+                        fprintf(stderr, "binary model round trip: block (%u,%u) differs\n", f1, f2);
+                        return 4;
+                    }
+                }
+            printf("binary-roundtrip ok\n");
+        }
     return 0;
 }

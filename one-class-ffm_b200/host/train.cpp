@@ -143,10 +143,11 @@ int main(int argc, char *argv[]) {
         // parse (in parallel) or reload the binary cache of an earlier parse
         auto load = [&](shared_ptr<ImpData> &d, bool has_label, const ImpLong *ds, const char *tag) {
             const string cpath = d->file_name + (ds ? string(".") + tag : string("")) + ".ocffm.bin";
-            if (opt.cache && d->load_cache(cpath)) return;
+            const vector<ImpLong> *filter = ds ? &U->Ds : nullptr;   // a test file is filtered by the training Ds
+            if (opt.cache && d->load_cache(cpath, filter)) return;
             d->read(has_label, ds);
             d->split_fields();
-            if (opt.cache) d->save_cache(cpath);
+            if (opt.cache) d->save_cache(cpath, filter);
         };
         load(U, true, nullptr, "tr");
         {   // the item file's labels come from transY, which must run before its fields are cached

@@ -91,6 +91,17 @@ SHAPES = {
                fu=[FieldSpec(2_500_000, id_like=True), FieldSpec(1_200_000, 2, 2, zipf=1.05)],
                fv=[FieldSpec(40_000, 1, 1), FieldSpec(35_000, 1, 1), FieldSpec(45_000, 1, 1),
                    FieldSpec(60_000, 3, 3)], pos=1.3, min_pos=1),
+    # C4 (KDD12-shaped) cut down for the oracle: same field structure (fu=2, fv=4 -> 8 cross pairs,
+    # id-like user field, Zipf query field whose top feature passes the default
+    # hot-replica threshold of 16 384 occurrences), ~1.3 positives per row
+    "C4s": dict(m=70_000, n=2_000,
+                fu=[FieldSpec(70_000, id_like=True), FieldSpec(5_000, 2, 2, zipf=1.05)],
+                fv=[FieldSpec(1_600, 1, 1), FieldSpec(1_400, 1, 1), FieldSpec(1_800, 1, 1),
+                    FieldSpec(2_400, 3, 3)], pos=1.3, min_pos=1),
+    # C3 (Outbrain-shaped) cut down: no id field at all, Zipf user fields, 1 positive per row, k=16
+    "C3s": dict(m=120_000, n=1_000,
+                fu=[FieldSpec(300, 3, 3, zipf=1.1), FieldSpec(14_000, 3, 3, zipf=1.05)],
+                fv=[FieldSpec(2_500, 3, 3), FieldSpec(400, 2, 2)], pos=1.0, min_pos=1),
 }
 
 

@@ -24,7 +24,11 @@ def run_validate(tc: bool, ds, prm, blocks):
         os.environ.pop("OCFFM_EVAL_TC", None)
 
 
-@pytest.mark.parametrize("shape,scale,k,rows", [("C1", 0.3, 16, 700), ("C1", 1.0, 32, 300)])
+# Kc = fu*fv*kp: 64 and 128 take the resident-A variant of k_score_topk_tc, 256 (C1 at k=64 -- the
+# C5 configuration -- and the 2x4-field C4-shaped slice at k=32 -- the north-star configuration)
+# the streaming-A variant (SmemTC<false>)
+@pytest.mark.parametrize("shape,scale,k,rows", [("C1", 0.3, 16, 700), ("C1", 1.0, 32, 300), ("C1", 1.0, 64, 300),
+                                                ("C4s", 1.0, 32, 300), ("C4s", 1.0, 64, 200)])
 def test_tc_scorer_matches_simt_and_oracle(shape, scale, k, rows):
     import synth
     ds = synth.generate(shape, seed=4, scale=scale, test_rows=rows, cold_rows=7)

@@ -1,0 +1,107 @@
+"""Parity on slices of the LARGE benchmark shapes (no parity run on C3/C4 shapes).
+
+C4s: KDD12-shaped (fu=2, fv=4 -> 8 cross pairs, Kc = 256 at k=32, Zipf query field whose top
+feature passes the DEFAULT hot-replica threshold).  C3s: Outbrain-shaped (no identity field at
+all, Zipf user fields, k=16).  Gradient / Hessian-vector per phase from identical state, one
+full outer iteration, and validate() (top-80 ids through the streaming-A tcgen05 scorer for
+Kc = 256) against the oracle.  The oracle side is computed once per shape."""
+import importlib
+
+import numpy as np
+import pytest
+
+import ocffm
+import pyoracle
+
+pytestmark = pytest.mark.gpu
+DT = {"f64": (ocffm.F64, 1e-9), "f32": (ocffm.F32, 1e-4)}
+SHAPES = {"C4s": 32, "C3s": 16}
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    assert a.shape == b.shape
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b)))) if a.size else 0.0
+
+
+def halves_of(fu, f):
+    # a user-side and an item-side half of: first cross pair, last cross pair, a user side block, an item side block
+    return [(0, fu, "W"), (0, fu, "H"), (fu - 1, f - 1, "W"), (fu - 1, f - 1, "H"), (0, 1, "W"), (1, 1, "H"),
+            (fu, f - 1, "H"), (f - 1, f - 1, "W")]
+
+
+@pytest.fixture(scope="module", params=sorted(SHAPES))
+def case(request):
+    synth = importlib.import_module("synth")
+    shape, k = request.param, SHAPES[request.param]
+    ds = synth.generate(shape, seed=3, test_rows=300, cold_rows=5)
+    prm = dict(k=k, lam=4.0, omega=2.0 ** -7, r=-1.0, self_side=True, freq=False)
+    o = pyoracle.Oracle(ds, **prm)
+    rng = np.random.default_rng(11)
+    blocks = {}
+    for f1, f2 in o.blocks():
+        for which in "WH":
+            w = rng.uniform(-0.05, 0.05, size=(o.block_rows(f1, f2, which), k))
+            blocks[(f1, f2, which)] = w
+            o.set_block(f1, f2, which, w)
+    o.init_state()
+    fu, f = ds.users.f, ds.users.f + ds.items.f
+    ref = dict(vec={v: o.vec(v) for v in ("a", "b", "sa", "sb", "ytilde_csr", "ytilde_csc")}, func0=o.func())
+    ref["grad"], ref["hv"] = {}, {}
+    for h in halves_of(fu, f):
+        G = o.grad(*h)
+        ref["grad"][h], ref["hv"][h] = G, o.hess_vec(*h, -G)
+    o.one_epoch()
+    ref["cg"] = o.cg_iters_total()
+    ref["func1"] = o.func()
+    ref["final"] = {(f1, f2, w): o.get_block(f1, f2, w) for f1, f2 in o.blocks() for w in "WH"}
+    ref["vec1"] = {v: o.vec(v) for v in ("a", "b", "ytilde_csr", "ytilde_csc")}
+    ref["val"] = o.validate(want_topk=True, want_scores=True)
+    o.close()
+    return shape, ds, prm, blocks, ref
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_big_shape_slice_against_oracle(case, dt):
+    shape, ds, prm, blocks, ref = case
+    dtype, tol = DT[dt]
+    p = ocffm.Problem(ds, dtype=dtype, **prm)        # default OCFFM_HOT_MIN: the Zipf field has hot features
+    for key, w in blocks.items():
+        p.set_block(*key, w)
+    p.init_state()
+    for v, want in ref["vec"].items():
+        assert rel_err(p.vec(v), want) <= tol, v
+    assert abs(p.objective() - ref["func0"]) <= max(tol, 1e-9) * abs(ref["func0"])
+    for h, G in ref["grad"].items():
+        assert rel_err(p.grad(*h), G) <= tol, ("grad", h)
+        assert rel_err(p.hess_vec(*h, -G), ref["hv"][h]) <= tol, ("hv", h)
+    p.reset_stats()
+    p.one_epoch()
+    cg = int(p.stats().cg_iters)
+    if dt == "f64":
+        assert cg == ref["cg"]
+    matched = cg == ref["cg"]
+    bound = 1e-8 if dt == "f64" else (1e-4 if matched else 1e-3)
+    assert abs(p.objective() - ref["func1"]) <= bound * abs(ref["func1"]), (cg, ref["cg"])
+    wtol = 1e-6 if dt == "f64" else (5e-3 if matched else 5e-2)
+    for key, want in ref["final"].items():
+        assert rel_err(p.get_block(*key), want) <= wtol, key
+    for v, want in ref["vec1"].items():
+        assert rel_err(p.vec(v), want) <= wtol, v
+    # ranking parity from the ORACLE's model (Kc = 256 on C4s: the streaming-A tcgen05 variant in fp32)
+    for key, want in ref["final"].items():
+        p.set_block(*key, want)
+    res, ro = p.validate(), ref["val"]
+    Z, mism = ro["Z"], 0
+    for i in range(ds.test_users.rows):
+        for rnk in range(80):
+            g, w = int(res["topk"][i, rnk]), int(ro["topk"][i, rnk])
+            if g != w:
+                mism += 1
+                assert g != 0xFFFFFFFF
+                assert abs(Z[i, g] - Z[i, w]) <= (1e-9 if dt == "f64" else 2e-5) * max(1.0, abs(Z[i, w])), (i, rnk, g, w)
+    assert mism <= 300 * 80 * 0.01, mism
+    if mism == 0:
+        assert rel_err(res["prec"], ro["prec"]) <= 1e-12 and rel_err(res["ndcg"], ro["ndcg"]) <= 1e-9
+    assert abs(res["ploss"] - ro["ploss"]) <= 10 * tol * abs(ro["ploss"])
+    p.close()

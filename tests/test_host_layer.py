@@ -79,3 +79,58 @@ def test_cli_fails_loudly_without_gpu():
     base = os.path.join(GOLDEN, "tiny", "tiny")
     r = run(["-k", "8", "-t", "1", base + ".item", base + ".tr"])
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_cache_is_rejected_when_stale():
+    """a test-set cache stores features already filtered by the TRAINING Ds; it must be
+    rejected when that filter changes, and any cache when its source text changed (size or mtime)."""
+    import shutil
+    base = os.path.join(GOLDEN, "tiny", "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = {}
+        for ext in ("item", "tr", "te"):
+            src[ext] = shutil.copy(base + "." + ext, os.path.join(tmp, "tiny." + ext))
+        subprocess.check_call([HOST_DUMP, src["item"], src["tr"], src["te"], os.path.join(tmp, "h.ocfd"), "8",
+                               "--side", "--via-cache", tmp])
+        d = load_golden("tiny")
+        ds = ",".join(str(int(x)) for x in d["U.Ds"])
+
+        def probe(cache, source, *filt):
+            return subprocess.check_output([HOST_DUMP, "--probe-cache", os.path.join(tmp, cache), source, *filt],
+                                           text=True).strip()
+        assert probe("T.bin", src["te"], ds) == "hit"
+        assert probe("U.bin", src["tr"]) == "hit"
+        grown = ",".join(str(int(x) + 1) for x in d["U.Ds"])
+        assert probe("T.bin", src["te"], grown) == "miss"        # training Ds changed -> old filtering is stale
+        assert probe("T.bin", src["te"]) == "miss"               # read without a filter != read with one
+        assert probe("U.bin", src["tr"], ds) == "miss"
+        st = os.stat(src["tr"])
+        os.utime(src["tr"], ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000_000))   # same size, newer
+        assert probe("U.bin", src["tr"]) == "miss"
+        with open(os.path.join(tmp, "old.bin"), "wb") as fh:     # a cache of the previous format
+            fh.write(b"OCFFMBIN1" + b"\0" * 64)
+        assert probe("old.bin", src["item"]) == "miss"
+
+
+@pytest.mark.parametrize("ns", [False, True])
+def test_binary_model_round_trip_on_host(ns):
+    """save_binary_model (reference layout, ffm.cpp:1239-1267) -> load_binary_model returns every block
+    bit for bit; a file written with/without --ns is refused by the other mode with a clear message."""
+    base = os.path.join(GOLDEN, "tiny", "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "m.bin")
+        out = subprocess.check_output([HOST_DUMP, base + ".item", base + ".tr", base + ".te", os.path.join(tmp, "h.ocfd"),
+                                       "8", "--ns" if ns else "--side", "--binary-roundtrip", path], text=True)
+        assert "binary-roundtrip ok" in out
+        # header of the reference layout: u32 f, fu, fv, k
+        hdr = np.fromfile(path, dtype=np.uint32, count=4)
+        assert list(hdr) == [4, 2, 2, 8]
+        r = run(["-k", "8", "--load", path, "--predict-only", "-p", base + ".te"] + ([] if ns else ["--ns"]) +
+                [base + ".item", base + ".tr"])
+        assert r.returncode == 1 and "--ns" in r.stderr and "layout mismatch" in r.stderr
+        bad = bytearray(open(path, "rb").read())
+        bad[0] = 7                                               # f != fu + fv
+        open(path, "wb").write(bytes(bad))
+        r = run(["-k", "8", "--load", path, "--predict-only", "-p", base + ".te"] + (["--ns"] if ns else []) +
+                [base + ".item", base + ".tr"])
+        assert r.returncode == 1 and "corrupt model file" in r.stderr

@@ -113,3 +113,31 @@ def test_grid_runner_matches_separate_runs():
                 # 6 printed digits; fp64 atomics may reorder sums, so allow the last digit to move
                 assert all(np.allclose(got[k], want[k], rtol=1e-5, atol=1e-9) for k in want), (l, w)
                 i += 1
+
+
+@pytest.mark.parametrize("case", ["tiny", "tiny_ns"])
+def test_binary_model_save_load_predict_round_trip(case):
+    """SURVEY 8(f1): `--save-binary` writes the reference's binary layout (ffm.cpp:1239-1267);
+    `--load <file> --predict-only` must then print the metrics the training run printed for its
+    last iteration (same model, same validate), and `--load` + more passes must continue from it."""
+    gdir = os.path.join(GOLDEN, case)
+    flags = open(os.path.join(gdir, "cli_flags.txt")).read().split()
+    base = os.path.join(gdir, case)
+    data = ["-c", "1", "-p", base + ".te", base + ".item", base + ".tr"]
+    with tempfile.TemporaryDirectory() as tmp:
+        mb, mt = os.path.join(tmp, "m.bin"), os.path.join(tmp, "m.txt")
+        a = subprocess.run([TRAIN] + flags + ["--f64", "--save-binary", mb, "-o", mt] + data, capture_output=True, text=True)
+        assert a.returncode == 0, a.stderr
+        last = [ln for ln in a.stdout.split("\n") if ln.strip()][-1]
+        mt2 = os.path.join(tmp, "m2.txt")
+        b = subprocess.run([TRAIN] + flags + ["--f64", "--load", mb, "--predict-only", "-o", mt2] + data,
+                           capture_output=True, text=True)
+        assert b.returncode == 0, b.stderr
+        pred = [ln for ln in b.stdout.split("\n") if ln.strip()][-1]
+        # same columns after the iteration number
+        assert numbers(last)[1:].tolist() == numbers(pred)[1:].tolist(), (last, pred)
+        assert open(mt).read() == open(mt2).read()       # the text model of the reloaded state is the same file
+        # the binary file itself: u32 f, fu, fv, k then u64 Ds (reference layout)
+        hdr = np.fromfile(mb, dtype=np.uint32, count=4)
+        want_hdr, _ = read_model(mt)
+        assert list(hdr) == want_hdr[:4]
