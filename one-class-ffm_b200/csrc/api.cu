@@ -326,11 +326,21 @@ struct Problem final : CtxBase {
     // OCFFM_FUSED_DOT=0: separate direction / regulariser+dot kernels per CG iteration (5 instead of 3)
     bool fused_dot = true;
     uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
+    // Per-row observed Gram for the Hessian passes of cross halves (rows.cu "Mrow").  Default: fp32
+    // contexts with kp 16 / 32 (at kp 64 building the Gram costs as much as the gathers it saves;
+    // fp64 contexts are the strict-parity mode and keep the reference's summation structure).
+    // OCFFM_MROW=0 off, =1 default rule, =2 also in fp64 contexts; OCFFM_MROW_MIN: pairs per heavy row
+    int mrow_mode = 1;
+    uint32_t mrow_min = 48;
+    size_t mrow_cap_bytes = size_t(3) << 30;
+    bool mrow_on = false, mrow_ready = false;
+    DevBuf<T> mrow;
+    uint64_t mrow_builds = 0;
     bool profile = false;
 
     struct Field {
         bool set = false;
-        uint64_t rows = 0, D = 0, nnz = 0;
+        uint64_t rows = 0, D = 0, nnz = 0, nnz_local = 0;
         DevBuf<uint32_t> rowptr, idx, hot_feat;
         DevBuf<T> val, freq, shadow;
         DevBuf<int16_t> hot_slot;
@@ -358,6 +368,16 @@ struct Problem final : CtxBase {
         std::vector<uint32_t> h_idx;
         OmegaView<T> view() const {
             return {wi_row.p, wi_beg.p, wi_cnt.p, n_items, rowptr.p, idx.p, yt.p, row0, row1, nnz_local};
+        }
+        // Per-row observed Gram (rows.cu "Mrow"): the local rows with >= mrow_min pairs are HEAVY --
+        // slot s of the Gram buffer belongs to row heavy_rows[s]; hw_* are the build items (<= 1024
+        // pairs each, rows split over several items come first and are the zeroed prefix
+        // [0, n_multi)); lw_* is the ordinary work-item list restricted to the other (LIGHT) rows.
+        DevBuf<uint32_t> heavy_rows, hw_slot, hw_beg, hw_cnt, lw_row, lw_beg, lw_cnt;
+        uint32_t n_heavy = 0, n_multi = 0, n_hw = 0, n_lw = 0;
+        uint64_t nnz_heavy = 0;
+        OmegaView<T> light_view() const {
+            return {lw_row.p, lw_beg.p, lw_cnt.p, n_lw, rowptr.p, idx.p, yt.p, row0, row1, nnz_local};
         }
     };
     struct Block {
@@ -436,6 +456,10 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_PEER_GATHER")) peer_gather_allowed = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_FUSED_DOT")) fused_dot = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
+        if (const char *e = getenv("OCFFM_MROW")) mrow_mode = atoi(e);
+        if (const char *e = getenv("OCFFM_MROW_MIN")) mrow_min = uint32_t(std::max(1, atoi(e)));
+        if (const char *e = getenv("OCFFM_MROW_CAP_MB")) mrow_cap_bytes = size_t(std::max(1, atoi(e))) << 20;
+        mrow_on = mrow_mode != 0 && row_gram_supported(int(kp)) && (std::is_same<T, float>::value || mrow_mode >= 2);
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_SLICE_CG")) slice_cg = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
@@ -555,6 +579,7 @@ struct Problem final : CtxBase {
         }
         F.row0 = lo(rows);
         F.row1 = hi(rows);
+        F.nnz_local = rowptr[F.row1] - rowptr[F.row0];
         F.set = true;
         sync();
         if (side == OCFFM_SIDE_T) { mt = rows; t_row0 = lo(rows); t_row1 = hi(rows); }
@@ -586,6 +611,7 @@ struct Problem final : CtxBase {
             }
         }
         Y.n_items = uint32_t(wr.size());
+        build_heavy_lists(Y, rowptr);
         Y.rowptr.upload(rp, st);
         Y.idx.upload(idx, Y.nnz, st);
         Y.wi_row.upload(wr, st);
@@ -595,6 +621,62 @@ struct Problem final : CtxBase {
         Y.yt.zero(st);
         Y.set = true;
         sync();
+    }
+
+    // heavy / light split of the local rows for the per-row Gram path (see Omega)
+    void build_heavy_lists(Omega &Y, const uint64_t *rowptr) {
+        Y.n_heavy = Y.n_multi = Y.n_hw = Y.n_lw = 0;
+        Y.nnz_heavy = 0;
+        if (!mrow_on) return;
+        const uint32_t kItem = 1024;
+        // raise the threshold until the Gram buffer fits the cap
+        uint64_t thr = mrow_min;
+        for (;;) {
+            uint64_t cntr = 0;
+            for (uint32_t i = Y.row0; i < Y.row1; ++i) cntr += (rowptr[i + 1] - rowptr[i]) >= thr;
+            if (cntr * kp * kp * sizeof(T) <= mrow_cap_bytes) break;
+            thr *= 2;
+        }
+        std::vector<uint32_t> multi, single;
+        for (uint32_t i = Y.row0; i < Y.row1; ++i) {
+            const uint64_t c = rowptr[i + 1] - rowptr[i];
+            if (c >= thr) (c > kItem ? multi : single).push_back(i);
+        }
+        // longest first: the build kernel's CTAs finish together
+        auto by_len = [&](uint32_t x, uint32_t y) { return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y]; };
+        std::stable_sort(multi.begin(), multi.end(), by_len);
+        std::stable_sort(single.begin(), single.end(), by_len);
+        std::vector<uint32_t> hr(multi);
+        hr.insert(hr.end(), single.begin(), single.end());
+        std::vector<uint32_t> hs, hb, hc, lr, lb, lc;
+        for (uint32_t s = 0; s < hr.size(); ++s) {
+            const uint64_t b0 = rowptr[hr[s]], e0 = rowptr[hr[s] + 1];
+            Y.nnz_heavy += e0 - b0;
+            const bool split = e0 - b0 > kItem;
+            for (uint64_t t = b0; t < e0; t += kItem) {
+                hs.push_back(s);
+                hb.push_back(uint32_t(t));
+                hc.push_back(uint32_t(std::min<uint64_t>(kItem, e0 - t)) | (split ? 0x80000000u : 0u));
+            }
+        }
+        for (uint32_t i = Y.row0; i < Y.row1; ++i) {
+            const uint64_t b0 = rowptr[i], e0 = rowptr[i + 1];
+            if (e0 - b0 >= thr) continue;
+            if (b0 == e0) { lr.push_back(i); lb.push_back(uint32_t(b0)); lc.push_back(0x80000000u); continue; }
+            for (uint64_t t = b0; t < e0; t += chunk) {
+                lr.push_back(i);
+                lb.push_back(uint32_t(t));
+                lc.push_back(uint32_t(std::min<uint64_t>(chunk, e0 - t)) | (t == b0 ? 0x80000000u : 0u));
+            }
+        }
+        Y.n_heavy = uint32_t(hr.size());
+        Y.n_multi = uint32_t(multi.size());
+        Y.n_hw = uint32_t(hs.size());
+        Y.n_lw = uint32_t(lr.size());
+        if (!Y.n_heavy) return;
+        Y.heavy_rows.upload(hr, st);
+        Y.hw_slot.upload(hs, st); Y.hw_beg.upload(hb, st); Y.hw_cnt.upload(hc, st);
+        Y.lw_row.upload(lr, st); Y.lw_beg.upload(lb, st); Y.lw_cnt.upload(lc, st);
     }
 
     void set_labels(uint64_t m_, const uint64_t *rowptr, const uint32_t *idx, const uint64_t *cp,
@@ -784,7 +866,7 @@ struct Problem final : CtxBase {
         col_sums<T>(Pc.p, Kc, Kc, 0, uint32_t(m), cs, st);
         convert_from_f64<T>(cs, vecKc.p, Kc, st);
         matvec_rows<T>(Qc.p, Kc, Kc, uint32_t(n), vecKc.p, sb.p, st);
-        algo_bytes += uint64_t(Fx) * (m + n) * k * sizeof(T) + (m + n) * sizeof(T);
+        algo_bytes += (uint64_t(Fx) * (m + n) * k * sizeof(T) + (m + n) * sizeof(T)) / uint64_t(comm.nranks);
     }
 
     void set_hyper(double lambda, double omega, double r) override {
@@ -863,6 +945,8 @@ struct Problem final : CtxBase {
         bool sliced;
         uint64_t s0, s1;
         size_t soff() const { return size_t(s0); }
+        // this rank's share of the half (statistics are per rank: the bench sums them over ranks)
+        uint64_t m1l, nnzYl, nnzXl, Dl;
     };
     Half half_of(uint32_t f1, uint32_t f2, int which) {
         OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
@@ -900,6 +984,10 @@ struct Problem final : CtxBase {
         h.sliced = comm.active() && h.X->identity && slice_cg;
         h.s0 = h.sliced ? h.X->row0 : 0;
         h.s1 = h.sliced ? h.X->row1 : h.D;
+        h.m1l = h.Yown->row1 - h.Yown->row0;
+        h.nnzYl = h.Yown->nnz_local;
+        h.nnzXl = h.X->nnz_local;
+        h.Dl = h.s1 - h.s0;
         return h;
     }
 
@@ -920,7 +1008,7 @@ struct Problem final : CtxBase {
         convert_from_f64<T>(out, GT.p, size_t(Kc) * kp, st);
         convert_from_f64<T>(cs, oQ.p, kp, st);
         convert_from_f64<T>(wsum, bQ.p, kp, st);
-        algo_bytes += h.n1 * k * sizeof(T) * (Fx + 1);
+        algo_bytes += uint64_t(r1 - r0) * k * sizeof(T) * (Fx + 1);
     }
     const T *qtq_of(const Half &h) const { return GT.p + size_t(h.bk->pair) * kp * kp; }
 
@@ -930,7 +1018,7 @@ struct Problem final : CtxBase {
         OC_CUDA(cudaMemsetAsync(G.p, 0, h.D * kp * sizeof(T), st));
         if (h.X->n_hot) h.X->shadow.zero(st);
         freshen(*h.Yown);
-        const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        const uint64_t nnzY = h.nnzYl, nnzX = h.nnzXl;
         if (h.side) {
             OC_CUDA(cudaMemsetAsync(ysum.p, 0, h.m1 * sizeof(T), st));
             ytilde_rowsum<T>(h.Yown->view(), ysum.p, kp, st);
@@ -938,7 +1026,7 @@ struct Problem final : CtxBase {
             reduce_sum<T>(h.b1, h.n1, 0, &sc->bsum, st);
             side_rows<T>(0, h.Yown->view(), h.X->view(), h.Q1, h.a1, h.sa1, ysum.p, &sc->bsum, nullptr,
                          T(prm.omega), T(prm.r), T(h.n1), G.p, kp, kNoGate, nullptr, st);
-            algo_bytes += nnzY * s + h.m1 * (k + 3) * s + nnzX * (4 + s) + 2 * h.D * k * s;
+            algo_bytes += nnzY * s + h.m1l * (k + 3) * s + nnzX * (4 + s) + 2 * h.Dl * k * s;
         } else {
             prepare_cross(h);
             const T *Ps = h.user ? Pc.p : Qc.p;
@@ -946,12 +1034,29 @@ struct Problem final : CtxBase {
             rowgemm<T>(Ps + size_t(r0) * Kc, Kc, Kc, GT.p, Tm.p + size_t(r0) * kp, r1 - r0, kp, kNoGate, st);
             grad_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, Tm.p, h.a1, oQ.p, bQ.p,
                                T(prm.omega), T(prm.r), G.p, kp, st);
-            algo_bytes += (h.m1 + 1) * 8 + nnzY * (4 + s) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
-                          uint64_t(Fx) * h.m1 * k * s + h.m1 * s + nnzX * (4 + s) + 2 * h.D * k * s;
+            algo_bytes += (h.m1l + 1) * 8 + nnzY * (4 + s) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
+                          uint64_t(Fx) * h.m1l * k * s + h.m1l * s + nnzX * (4 + s) + 2 * h.Dl * k * s;
         }
         if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, G.p, kp, st);
         if (!h.sliced) comm.allreduce(G.p, h.D * kp, st);
         nnz_trav += nnzY + nnzX;
+    }
+
+    // M_i = sum_{j in Omega_i} q_j q_j^T for the heavy rows of this half (Q1 is fixed during the half
+    // solve, ffm.cpp:744-813), so that every CG iteration streams kp x kp numbers per heavy row
+    // instead of gathering |Omega_i| rows of Q1
+    void build_mrow(const Half &h) {
+        mrow_ready = false;
+        if (!mrow_on || h.side) return;
+        const Omega &Y = *h.Yown;
+        if (!Y.n_heavy) return;
+        mrow.ensure(size_t(Y.n_heavy) * kp * kp);
+        if (Y.n_multi) OC_CUDA(cudaMemsetAsync(mrow.p, 0, size_t(Y.n_multi) * kp * kp * sizeof(T), st));
+        row_gram<T>(Y.hw_slot.p, Y.hw_beg.p, Y.hw_cnt.p, Y.n_hw, Y.idx.p, h.Q1, h.ldq, mrow.p, int(kp), st);
+        algo_bytes += Y.nnz_heavy * 4 + gather_bytes(h.n1 * k * sizeof(T), Y.nnz_heavy, k * sizeof(T)) +
+                      uint64_t(Y.n_heavy) * k * k * sizeof(T);
+        mrow_ready = true;
+        ++mrow_builds;
     }
 
     size_t hv_event_pair() {
@@ -998,8 +1103,16 @@ struct Problem final : CtxBase {
                 ev = hv_event_pair();
                 OC_CUDA(cudaEventRecord(hv_events[ev].first, st));
             }
-            hess_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega), Hv.p,
-                               kp, gate, dot_out, st);
+            if (mrow_ready) {
+                // heavy rows from their Gram blocks, the light rows by gathers
+                hess_heavy_rows<T>(h.Yown->heavy_rows.p, h.Yown->n_heavy, h.X->view(), mrow.p, V.p, VQ.p,
+                                   T(prm.omega), Hv.p, int(kp), gate, dot_out, st);
+                hess_cross_rows<T>(h.Yown->light_view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega),
+                                   Hv.p, kp, gate, dot_out, st);
+            } else {
+                hess_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega), Hv.p,
+                                   kp, gate, dot_out, st);
+            }
             if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
         }
         if (h.X->n_hot) fold_hot<T>(h.X->shadow.p, h.X->hot_feat.p, h.X->n_hot, Hv.p, kp, st);
@@ -1019,21 +1132,21 @@ struct Problem final : CtxBase {
     }
     void account_hess(const Half &h, uint64_t iters) {
         const size_t s = sizeof(T);
-        const uint64_t nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        const uint64_t nnzY = h.nnzYl, nnzX = h.nnzXl;
         if (h.side) {
-            algo_bytes += iters * (nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) + h.m1 * k * s +
-                                   h.m1 * 4 + h.D * k * s);
+            algo_bytes += iters * (nnzX * (4 + s) + gather_bytes(h.Dl * k * s, nnzX, k * s) + h.m1l * k * s +
+                                   h.m1l * 4 + h.Dl * k * s);
             nnz_trav += iters * nnzX;
         } else {
-            const uint64_t bytes = (h.m1 + 1) * 8 + nnzX * (4 + s) +
-                                   gather_bytes(h.D * k * s, nnzX, k * s) + nnzY * 4 +
-                                   gather_bytes(h.n1 * k * s, nnzY, k * s) + h.D * k * s;
+            const uint64_t bytes = (h.m1l + 1) * 8 + nnzX * (4 + s) +
+                                   gather_bytes(h.Dl * k * s, nnzX, k * s) + nnzY * 4 +
+                                   gather_bytes(h.n1 * k * s, nnzY, k * s) + h.Dl * k * s;
             algo_bytes += iters * bytes;
             hv_algo_bytes += iters * bytes;
             hv_launches += iters;
             nnz_trav += iters * (nnzY + nnzX);
         }
-        algo_bytes += iters * 7 * h.D * k * s;
+        algo_bytes += iters * 7 * h.Dl * k * s;
     }
 
     // cg, ffm.cpp:744-813.  G holds the gradient WITHOUT lambda W when add_reg is set (solver
@@ -1078,6 +1191,7 @@ struct Problem final : CtxBase {
     int run_cg(const Half &h, bool add_reg) {
         const size_t o = h.soff() * kp;
         const T *fq = h.freq ? h.freq + h.soff() : nullptr;
+        build_mrow(h);
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
         cg_init<T>(G.p + o, h.W1 + o, fq, add_reg ? T(prm.lambda) : T(0), R.p + o, V.p + o, S.p + o, h.s1 - h.s0,
                    kp, sc, st);
@@ -1110,7 +1224,7 @@ struct Problem final : CtxBase {
     // update_side / update_cross, ffm.cpp:405-465
     void apply_update(const Half &h) {
         const size_t s = sizeof(T);
-        const uint64_t len = h.D * kp, nnzY = h.Yown->nnz, nnzX = h.X->nnz;
+        const uint64_t len = h.D * kp, nnzY = h.nnzYl, nnzX = h.nnzXl;
         // sliced half: one all-gather of the step per half solve, then every rank applies the whole
         // step to its replicas (W, P, a) with the single-rank kernels
         if (h.sliced) {
@@ -1133,15 +1247,15 @@ struct Problem final : CtxBase {
         if (h.side) {
             ytilde_add_gap<T>(h.Yown->view(), gap.p, 1, st);
             if (!mirror_yt) ytilde_add_gap<T>(h.Yoth->view(), gap.p, 0, st);
-            algo_bytes += 3 * h.D * k * s + nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) +
-                          4 * h.m1 * k * s + copies * (nnzY * (4 + 2 * s) + h.m1 * s);
+            algo_bytes += 3 * h.Dl * k * s + nnzX * (4 + s) + gather_bytes(h.Dl * k * s, nnzX, k * s) +
+                          4 * h.m1l * k * s + copies * (nnzY * (4 + 2 * s) + h.m1l * s);
         } else {
             sddmm_add<T>(h.Yown->view(), XS.p, kp, h.Q1, h.ldq, kp, st);
             if (!mirror_yt) sddmm_add<T>(h.Yoth->view(), h.Q1, h.ldq, XS.p, kp, kp, st);
-            algo_bytes += 3 * h.D * k * s + nnzX * (4 + s) + gather_bytes(h.D * k * s, nnzX, k * s) +
-                          4 * h.m1 * k * s +
+            algo_bytes += 3 * h.Dl * k * s + nnzX * (4 + s) + gather_bytes(h.Dl * k * s, nnzX, k * s) +
+                          4 * h.m1l * k * s +
                           copies * (nnzY * (4 + 2 * s)) + gather_bytes(h.n1 * k * s, nnzY, k * s) +
-                          (copies - 1) * gather_bytes(h.m1 * k * s, nnzY, k * s);
+                          (copies - 1) * gather_bytes(h.m1l * k * s, nnzY, k * s);
         }
         // the reference's traversal count (both copies, ffm.cpp:423-436, 451-464)
         nnz_trav += 2 * nnzY + nnzX;
@@ -1244,6 +1358,7 @@ struct Problem final : CtxBase {
         OC_REQUIRE(rows == h.D, "rows must equal Ds of the updated field");
         upload_padded(V, Vin, h.D);
         if (!h.side) prepare_cross(h);
+        build_mrow(h);
         OC_CUDA(cudaMemsetAsync(Hv.p, 0, h.D * kp * sizeof(T), st));
         hess_scatter(h, kNoGate);
         if (h.sliced) comm.allgather_rows(Hv.p, h.D, kp, st);

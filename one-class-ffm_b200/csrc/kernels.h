@@ -133,6 +133,16 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
 template <typename T>
 void fold_hot(const T *shadow, const uint32_t *hot_feat, uint32_t n_hot, T *Out, int kp, cudaStream_t s);
 
+// Per-row observed Gram (rows.cu "Mrow"): M[slot] = sum over the nnz of an item of q_j q_j^T, and the
+// hs_cross pass of the heavy rows from it (z_i = (1-w) M_i phi_i + w tau_i, Hv += X_i^T z_i).
+bool row_gram_supported(int kp);
+template <typename T>
+void row_gram(const uint32_t *it_slot, const uint32_t *it_beg, const uint32_t *it_cnt, uint32_t n_items,
+              const uint32_t *yidx, const T *Q1, uint32_t ldq, T *M, int kp, cudaStream_t s);
+template <typename T>
+void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView<T> &X, const T *M, const T *V,
+                     const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, cudaStream_t s);
+
 // ---- dense.cu --------------------------------------------------------------------------------
 // Out64[Kc x kp] += A[rows x Kc]^T B[rows x kp]; colsum64[0:kp] += B^T 1 ; wsum64[0:kp] += B^T wvec
 // (mm(a,b,c,k,l) ffm.cpp:41-45 for all cross pairs at once + mv ffm.cpp:660-661)

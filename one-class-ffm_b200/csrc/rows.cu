@@ -468,6 +468,164 @@ k_fold_hot(const T *__restrict__ shadow, const uint32_t *__restrict__ hot_feat, 
     st4(dst, o);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Per-row observed Gram ("Mrow").  The Omega term of hs_cross (ffm.cpp:722-736) for row i is
+//   sum_{j in Omega_i} (phi_i . q_j) q_j = M_i phi_i,   M_i = sum_{j in Omega_i} q_j q_j^T  (k x k),
+// and Q1 does not change during a half solve (ffm.cpp:744-813 works on one block), so for rows
+// with many observed pairs M_i is built ONCE per half solve (k_row_gram) and every CG iteration
+// streams kp*kp numbers per row from HBM (k_hess_heavy) instead of gathering |Omega_i| rows of
+// Q1 through L2/L1 -- the gather pass was bound by L1TEX wavefronts and load latency, this one
+// by HBM bandwidth.  Rows with few pairs stay on the gather path (k_hess_cross on the light list).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int N>
+__device__ __forceinline__ void load_n(const T *p, T (&o)[N]) {
+    if constexpr (sizeof(T) == 4 && N == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        o[0] = v.x; o[1] = v.y;
+    } else if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            const V4<T> v = ldg4(p + i);
+            o[i] = v.x; o[i + 1] = v.y; o[i + 2] = v.z; o[i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) o[i] = __ldg(p + i);
+    }
+}
+
+// acc[r][c] += a[r] * b[c]; fp32 uses the packed FFMA2 of sm_100 (two FMAs per issue slot)
+template <typename T, int TR, int TC>
+__device__ __forceinline__ void outer_acc(T (&acc)[TR][TC], const T (&a)[TR], const T (&b)[TC]) {
+    if constexpr (sizeof(T) == 4 && TC % 2 == 0) {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+            const float2 ar = make_float2(a[r], a[r]);
+#pragma unroll
+            for (int c = 0; c < TC; c += 2) {
+                const float2 v = __ffma2_rn(ar, make_float2(b[c], b[c + 1]), make_float2(acc[r][c], acc[r][c + 1]));
+                acc[r][c] = v.x;
+                acc[r][c + 1] = v.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int c = 0; c < TC; ++c) acc[r][c] += a[r] * b[c];
+    }
+}
+
+// One warp per item: item w covers nnz [beg[w], beg[w] + (cnt[w] & 0x7fffffff)) of the heavy row in
+// slot[w]; bit 31 of cnt: the row is split over several items, accumulate with REDs into the
+// pre-zeroed M[slot] (otherwise the item is the whole row and M[slot] is simply stored).
+// Lane (a, b) = (lane / 4, lane % 4) owns the TR x TC tile at (a*TR, b*TC) of the kp x kp matrix.
+template <typename T, int KP>
+__global__ void __launch_bounds__(kThreads)
+k_row_gram(const uint32_t *__restrict__ it_slot, const uint32_t *__restrict__ it_beg,
+           const uint32_t *__restrict__ it_cnt, uint32_t n_items, const uint32_t *__restrict__ yidx,
+           const T *__restrict__ Q1, uint32_t ldq, T *__restrict__ M) {
+    pdl_enter();
+    constexpr int TR = KP / 8, TC = KP / 4, U = 4;
+    const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (item >= n_items) return;
+    const uint32_t slot = it_slot[item], beg = it_beg[item], c = it_cnt[item];
+    const uint32_t cnt = c & 0x7fffffffu;
+    const uint32_t a = lane >> 2, b = lane & 3u;
+    T acc[TR][TC];
+#pragma unroll
+    for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int cc = 0; cc < TC; ++cc) acc[r][cc] = T(0);
+    const T *qa_base = Q1 + a * TR, *qb_base = Q1 + b * TC;
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t nb = min(32u, cnt - base);
+        const uint32_t jl = lane < nb ? yidx[beg + base + lane] : 0u;
+        for (uint32_t u0 = 0; u0 < nb; u0 += U) {
+            T qa[U][TR], qb[U][TC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {   // entries past nb re-read row yidx -> 0 and contribute nothing
+                const size_t off = size_t(__shfl_sync(0xffffffffu, jl, (u0 + u) & 31u)) * ldq;
+                load_n<T, TR>(qa_base + off, qa[u]);
+                load_n<T, TC>(qb_base + off, qb[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u0 + u >= nb) {
+#pragma unroll
+                    for (int r = 0; r < TR; ++r) qa[u][r] = T(0);
+                }
+                outer_acc<T, TR, TC>(acc, qa[u], qb[u]);
+            }
+        }
+    }
+    T *out = M + size_t(slot) * KP * KP + size_t(a * TR) * KP + b * TC;
+    if (c >> 31) {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int cc = 0; cc < TC; cc += 4)
+                red4(out + r * KP + cc, V4<T>{acc[r][cc], acc[r][cc + 1], acc[r][cc + 2], acc[r][cc + 3]});
+    } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int cc = 0; cc < TC; cc += 4)
+                st4(out + r * KP + cc, V4<T>{acc[r][cc], acc[r][cc + 1], acc[r][cc + 2], acc[r][cc + 3]});
+    }
+}
+
+// hs_cross for the heavy rows (one warp per row): z_i = (1-w) M_i phi_i + w tau_i, Hv += X_i^T z_i.
+// The kp x kp matrix is read with fully coalesced 16-byte loads: a group of G = kp/4 lanes takes one
+// matrix row per step, the 32/G groups of the warp take rows g*STEPS + step; after the group
+// reduction lane (g, lg < STEPS) owns component g*STEPS + lg of z.
+template <typename T, int KP>
+__global__ void __launch_bounds__(kThreads)
+k_hess_heavy(const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy, CsrView<T> X,
+             const T *__restrict__ M, const T *__restrict__ V, const T *__restrict__ VQ, T w,
+             T *__restrict__ Hv, Gate gate, double *__restrict__ dot_out) {
+    pdl_enter();
+    constexpr int G = KP / 4, NG = 32 / G, STEPS = KP / NG;
+    static_assert(STEPS <= G, "every component of z needs an owner lane");
+    if (!gate_open(gate)) return;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    T vhv = T(0);
+    if (slot < n_heavy) {
+        const uint32_t row = heavy_rows[slot];
+        const uint32_t g = lane / G, lg = lane % G;
+        const bool owner = lg < uint32_t(STEPS);
+        const uint32_t zi = g * STEPS + (owner ? lg : 0u);
+        const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
+        V4<T> phi4 = zero4<T>();
+        T phi_o = T(0), tau_o = T(0);
+        for (uint32_t t = xb; t < xe; ++t) {
+            const size_t off = size_t(X.identity ? row : X.idx[t]) * KP;
+            const T v = X.val[t];
+            fma4(phi4, v, ldg4(V + off + lg * 4));
+            phi_o += v * __ldg(V + off + zi);
+            tau_o += v * __ldg(VQ + off + zi);
+        }
+        const T *Mi = M + size_t(slot) * KP * KP + size_t(g * STEPS) * KP + lg * 4;
+        T d[STEPS];
+#pragma unroll
+        for (int cstep = 0; cstep < STEPS; ++cstep) d[cstep] = dot4(ldg4(Mi + cstep * KP), phi4);
+        T mine = T(0);
+#pragma unroll
+        for (int cstep = 0; cstep < STEPS; ++cstep) {
+            const T sum = gsum<G>(d[cstep], 0xffffffffu);
+            if (lg == uint32_t(cstep)) mine = sum;
+        }
+        if (owner) {
+            const T z = (T(1) - w) * mine + w * tau_o;
+            vhv = phi_o * z;
+            for (uint32_t t = xb; t < xe; ++t)
+                atomicAdd(scatter_row(X, Hv, X.identity ? row : X.idx[t], KP) + zi, z * X.val[t]);
+        }
+    }
+    if (dot_out) warp_add_slot(double(vhv), dot_out, kDotSlots);
+}
+
 inline unsigned blocks_for(uint64_t groups, int G) {
     const uint64_t threads = groups * uint64_t(G);
     return unsigned((threads + kThreads - 1) / kThreads);
@@ -595,6 +753,35 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
                                 out, accumulate));
 }
 
+
+bool row_gram_supported(int kp) { return kp == 16 || kp == 32; }
+
+template <typename T>
+void row_gram(const uint32_t *it_slot, const uint32_t *it_beg, const uint32_t *it_cnt, uint32_t n_items,
+              const uint32_t *yidx, const T *Q1, uint32_t ldq, T *M, int kp, cudaStream_t s) {
+    if (!n_items) return;
+    const unsigned blocks = unsigned((uint64_t(n_items) * 32 + kThreads - 1) / kThreads);
+    if (kp == 32)
+        OC_LAUNCH((k_row_gram<T, 32>), blocks, kThreads, 0, s, it_slot, it_beg, it_cnt, n_items, yidx, Q1, ldq, M);
+    else if (kp == 16)
+        OC_LAUNCH((k_row_gram<T, 16>), blocks, kThreads, 0, s, it_slot, it_beg, it_cnt, n_items, yidx, Q1, ldq, M);
+    else
+        throw Error(-6, "per-row Gram needs a padded latent dimension of 16 or 32");
+}
+
+template <typename T>
+void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView<T> &X, const T *M, const T *V,
+                     const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, cudaStream_t s) {
+    if (!n_heavy) return;
+    const unsigned blocks = unsigned((uint64_t(n_heavy) * 32 + kThreads - 1) / kThreads);
+    if (kp == 32)
+        OC_LAUNCH((k_hess_heavy<T, 32>), blocks, kThreads, 0, s, heavy_rows, n_heavy, X, M, V, VQ, w, Hv, gate, dot_out);
+    else if (kp == 16)
+        OC_LAUNCH((k_hess_heavy<T, 16>), blocks, kThreads, 0, s, heavy_rows, n_heavy, X, M, V, VQ, w, Hv, gate, dot_out);
+    else
+        throw Error(-6, "per-row Gram needs a padded latent dimension of 16 or 32");
+}
+
 #define OC_INSTANTIATE(T)                                                                          \
     template void spmm_rows<T>(const CsrView<T> &, const T *, T *, uint32_t, int, cudaStream_t);   \
     template void spmm_update<T>(const CsrView<T> &, const T *, T *, T *, uint32_t, const T *, T *, \
@@ -616,7 +803,11 @@ void rowwise_dot(const T *P, const T *Q, uint32_t rows, int kp, T *out, int accu
                                     const T *, T, T, T, int, int, SolveScalars *, cudaStream_t);   \
     template void ytilde_add_gap<T>(const OmegaView<T> &, const T *, int, cudaStream_t);           \
     template void rowwise_dot<T>(const T *, const T *, uint32_t, int, T *, int, cudaStream_t);     \
-    template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);
+    template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);         \
+    template void row_gram<T>(const uint32_t *, const uint32_t *, const uint32_t *, uint32_t,      \
+                              const uint32_t *, const T *, uint32_t, T *, int, cudaStream_t);      \
+    template void hess_heavy_rows<T>(const uint32_t *, uint32_t, const CsrView<T> &, const T *,    \
+                                     const T *, const T *, T, T *, int, Gate, double *, cudaStream_t);
 
 OC_INSTANTIATE(float)
 OC_INSTANTIATE(double)

@@ -66,3 +66,66 @@ def test_schedule_knobs_do_not_change_results(self_side):
     # sums of the two orientations agree exactly up to ordering
     assert abs(float(np.sum(base["csr"])) - float(np.sum(base["csc"]))) <= 1e-9 * abs(float(np.sum(base["csr"])))
     assert np.array_equal(np.sort(base["csr"]), np.sort(base["csc"]))
+
+
+@pytest.mark.parametrize("k,mrow_min", [(32, 4), (16, 4), (32, 48), (12, 2)])
+def test_per_row_gram_path_matches_gather_path(k, mrow_min, monkeypatch):
+    """Per-row observed Gram (rows.cu "Mrow"): heavy rows take M_i phi_i from a kp x kp block built
+    once per half solve, light rows gather.  Forced on in fp64 (OCFFM_MROW=2) with a low threshold so
+    that the small set has heavy rows of every kind (single item, rows split over several build
+    items, empty rows in the light list): Hessian-vector products against the oracle, and a full
+    outer iteration against the gather-only path."""
+    synth = importlib.import_module("synth")
+    ds = synth.generate("C1", seed=6, scale=1.0 if mrow_min <= 4 else 0.5, test_rows=50, pos_override=14.0)
+    prm = dict(k=k, lam=4.0, omega=2.0 ** -7, r=-1.0, self_side=True, freq=False)
+    o = pyoracle.Oracle(ds, **prm)
+    res = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("OCFFM_MROW", mode)
+        monkeypatch.setenv("OCFFM_MROW_MIN", str(mrow_min))
+        p = ocffm.Problem(ds, dtype=ocffm.F64, **prm)
+        model = p.init_model(seed=4)
+        if mode == "2":
+            for (f1, f2, which), w in model.items():
+                o.set_block(f1, f2, which, w)
+            o.init_state()
+        p.init_state()
+        fu = p.fu
+        hv = {}
+        for h in [(0, fu, "W"), (0, fu, "H"), (1, fu + 1, "W"), (1, fu + 1, "H"), (0, fu + 1, "H")]:
+            G = o.grad(*h)
+            want = o.hess_vec(*h, -G)
+            got = p.hess_vec(*h, -G)
+            assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want)), (mode, h)
+            hv[h] = got
+        p.one_epoch()
+        res[mode] = dict(cg=int(p.stats().cg_iters), obj=p.objective(), hv=hv)
+        p.close()
+    o.one_epoch()
+    assert res["0"]["cg"] == o.cg_iters_total()
+    assert res["2"]["cg"] == res["0"]["cg"]
+    assert abs(res["2"]["obj"] - res["0"]["obj"]) <= 1e-10 * abs(res["0"]["obj"])
+    assert abs(res["2"]["obj"] - o.func()) <= 1e-9 * abs(o.func())
+
+
+def test_per_row_gram_path_fp32_default(monkeypatch):
+    """fp32 contexts take the per-row Gram path by default (threshold 48 pairs per row): same
+    tolerance as every other fp32 phase (1e-4 relative, north_star)."""
+    synth = importlib.import_module("synth")
+    ds = synth.generate("C1", seed=7, scale=0.5, test_rows=50, pos_override=60.0)
+    prm = dict(k=32, lam=4.0, omega=2.0 ** -7, r=-1.0, self_side=False, freq=False)
+    o = pyoracle.Oracle(ds, **prm)
+    p = ocffm.Problem(ds, dtype=ocffm.F32, **prm)
+    for (f1, f2, which), w in p.init_model(seed=4).items():
+        o.set_block(f1, f2, which, w)
+    o.init_state()
+    p.init_state()
+    fu = p.fu
+    for h in [(0, fu, "W"), (0, fu, "H"), (1, fu + 1, "W"), (1, fu, "H")]:
+        G = o.grad(*h)
+        want, got = o.hess_vec(*h, -G), p.hess_vec(*h, -G)
+        assert np.max(np.abs(got - want)) <= 1e-4 * np.max(np.abs(want)), h
+    o.one_epoch()
+    p.one_epoch()
+    ro, rp = o.func(), p.objective()     # the restatement's objective also covers --ns (cross pairs only)
+    assert abs(rp - ro) <= 1e-3 * abs(ro)
