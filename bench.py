@@ -39,7 +39,14 @@ WORKLOADS = {
     "C5": ("C2", 64, 30_000),   # BASELINE configs[4]: d=64 KKBox-shaped scoring + top-k sweep (see "eval")
 }
 SHAPE_M = {"C1": 10_000, "C2": 30_000, "C3": 8_000_000, "C4": 4_000_000, "C5": 30_000}
-CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02, "C5": 0.1}
+CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02, "C5": 0.1}      # cpu_baseline leg of the GPU arm
+# --impl reference: the headline workload runs at FULL size (same config as the GPU arm, fewer timed
+# iterations); the multi-million-row shapes stay on a stated sub-sample
+REF_ARM_SCALE = {"C2": 1.0, "C1": 1.0, "C3": 0.02, "C4": 0.02, "C5": 0.1}
+REF_ARM_MAX_STEPS = 3
+# BASELINE configs[2..4] shard ONE fixed set over the GPUs (strong scaling); the headline C2 run keeps
+# round 1's weak scaling (one block of 30 000 users per GPU over the same items)
+DEFAULT_SCALING = {"C2": "weak", "C1": "strong", "C3": "strong", "C4": "strong", "C5": "strong"}
 
 
 def peaks():
@@ -151,8 +158,9 @@ def run_reference_arm(args, shape, k, test_rows):
         harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(harness):
         return run_port_arm(args, shape, k, test_rows)
-    scale = args.cpu_scale or CPU_SAMPLE_SCALE[args.workload]
-    ds = synth.generate(shape, seed=args.seed, scale=scale, test_rows=max(64, int(test_rows * scale * 0.1)))
+    scale = args.cpu_scale or (REF_ARM_SCALE if args.impl == "reference" else CPU_SAMPLE_SCALE)[args.workload]
+    # the evaluator is timed on a bounded number of test rows (the reference ranks ~50-900 users/s)
+    ds = synth.generate(shape, seed=args.seed, scale=scale, test_rows=min(1000, max(64, int(test_rows * scale * 0.1))))
     ncpu = os.cpu_count() or 1
     threads = args.cpu_threads or min(ncpu, 16)
     epochs = args.warmup + args.steps
@@ -207,8 +215,15 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = one block of the shape's users per GPU, strong = the fixed shape sharded")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the 1-rank vs N-rank fp64 self-check")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
+    else:   # bounded: the whole reference run must end within a few minutes
+        args.warmup, args.steps = 1, max(1, min(args.steps, REF_ARM_MAX_STEPS))
+    scaling = args.scaling or DEFAULT_SCALING[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,7 +244,7 @@ def main():
         config.update(sample=ref["sample"])
         line = dict(metric="nnz_per_s", value=ref["value"], unit="nnz/s", n_gpus=0, steps=args.steps,
                     warmup=args.warmup, ms_per_step=1e3 * ref["sec_per_epoch"], higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                    scaling=scaling, vs_baseline=None, dtype="f64", data="synthetic", config=config,
                     impl="reference", sec_per_outer_iteration=ref["sec_per_epoch"],
                     eval_users_per_s=ref["eval_users_per_s"], gpu_launches=0,
                     cpu_baseline=dict(value=ref["value"], unit="nnz/s", cores=ref["cores"], kind=ref["kind"],
@@ -254,7 +269,7 @@ def main():
 
     t_gen = time.time()
     n_test = 0 if args.no_eval else max(64, int(test_rows * args.scale))
-    if world > 1:
+    if world > 1 and scaling == "weak":
         # WEAK scaling: every GPU brings one block of the shape's users (m = 30k x N for C2) over
         # the same items; each rank generates its own seeded block, blocks are exchanged through
         # /tmp (one node), every rank assembles the full set (it needs both orientations of Omega)
@@ -275,11 +290,13 @@ def main():
             for b in range(world):
                 os.remove(f"{tag}_b{b}.pkl")
     else:
+        # one GPU, or STRONG scaling: every rank builds the same seeded set and keeps its row slices
         ds = synth.generate(shape=shape, seed=args.seed, scale=args.scale, test_rows=n_test)
     t_gen = time.time() - t_gen
     config.update(m=ds.m, n=ds.n, nnz_y=int(ds.train.idx.size), fu=ds.users.f, fv=ds.items.f,
                   m_t=0 if ds.test is None else ds.test.rows, parallelism=f"rows sharded over {world} GPU(s)" + (
-                      "" if world == 1 else f"; weak scaling: {world} blocks of {SHAPE_M.get(shape, 0)} users over the same items"))
+                      "" if world == 1 else (f"; weak scaling: {world} blocks of {SHAPE_M.get(shape, 0)} users over the same items"
+                                             if scaling == "weak" else "; strong scaling: the fixed shape sharded by rows")))
     dtype = ocffm.F32 if args.dtype == "f32" else ocffm.F64
     os.environ.setdefault("OCFFM_PROFILE", "1")     # CUDA events around every hv_cross launch
     prob = ocffm.Problem(ds, k=k, dtype=dtype, device=local_rank, self_side=not args.ns, comm=comm, **HYPER)
@@ -310,25 +327,37 @@ def main():
     st = prob.stats()
     ms = dist_util.max_over_ranks(ms)
     sec = ms / 1e3
-    value = st.nnz_traversed / sec
+    # the library's counters are per rank (this rank's rows): the job's totals are sums over ranks
+    nnz_total, cg_total_max, algo_total = dist_util.sum_over_ranks(float(st.nnz_traversed)), st.cg_iters, \
+        dist_util.sum_over_ranks(float(st.algo_bytes))
+    value = nnz_total / sec
     objective = prob.objective()
 
     pk = peaks()
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_hv_traffic.json")
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_hv_traffic.json")
     if args.workload == "C2" and world == 1 and os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh)["traffic_bytes_per_launch_avg"]   # ncu dram read+write per launch
+        traffic_src = "profiles/r02_hv_traffic.json (one ncu --set full capture of the same command, NOT measured in this run)"
+    # PER-GPU roofline: this rank's algorithmic bytes over this rank's kernel time against ONE GPU's peak
     hv_gbs = (st.hv_algo_bytes / 1e9) / (st.hv_ms / 1e3) if st.hv_ms > 0 else None
-    roofline = dict(bound="hbm", kernel="k_hess_cross (hs_cross row pass)", achieved=hv_gbs, peak=pk["hbm_gbs"],
+    roofline = dict(bound="hbm", kernel="hs_cross row pass: k_hess_heavy (per-row Gram blocks streamed) + k_hess_cross "
+                    "(gathers, light rows)" if st.row_gram_builds else "k_hess_cross (hs_cross row pass)",
+                    achieved=hv_gbs, peak=pk["hbm_gbs"],
                     unit="GB/s", frac=(hv_gbs / pk["hbm_gbs"]) if hv_gbs else None, traffic=traffic,
+                    traffic_source=traffic_src, per_gpu=True,
                     peak_source=pk["source"], launches=int(st.hv_launches),
                     avg_launch_ms=(st.hv_ms / st.hv_launches) if st.hv_launches else None,
                     share_of_step=(st.hv_ms / ms) if ms > 0 else None,
                     algo_bytes_per_launch=(st.hv_algo_bytes / st.hv_launches) if st.hv_launches else None,
-                    gather_gbs=(st.hv_launches * ds.train.idx.size * k * (4 if args.dtype == "f32" else 8) / 1e9)
-                    / (st.hv_ms / 1e3) if st.hv_ms > 0 else None,
-                    whole_epoch_gbs=(st.algo_bytes / 1e9) / sec)
+                    whole_epoch_gbs_per_gpu=(st.algo_bytes / 1e9) / sec,
+                    whole_epoch_frac_per_gpu=(st.algo_bytes / 1e9) / sec / pk["hbm_gbs"],
+                    whole_epoch_gbs_all_gpus=(algo_total / 1e9) / sec,
+                    row_gram_builds=int(st.row_gram_builds), row_gram_bytes=int(st.row_gram_bytes))
+    free_b, total_b = torch.cuda.mem_get_info(local_rank)
+    footprint = dict(omega_device_bytes=int(st.omega_device_bytes), hbm_used_bytes=int(total_b - free_b),
+                     note="per rank (rank 0): Omega slices = row pointers, column ids, y-tilde and work-item lists of both orientations")
 
     # ---- evaluation (validate, ffm.cpp:925-1016) --------------------------------------------
     eval_info = None
@@ -352,11 +381,13 @@ def main():
                          n_ranked=ds.train.n_items, tflops=alg_tflops,
                          roofline=dict(bound="tensor", kernel="k_score_topk_tc (tcgen05 kind::tf32, 3xTF32)"
                                        if args.dtype == "f32" else "k_score_topk (SIMT)",
-                                       achieved=3.0 * alg_tflops if args.dtype == "f32" else alg_tflops,
-                                       peak=tf32_peak, unit="TFLOP/s",
-                                       frac=(3.0 * alg_tflops if args.dtype == "f32" else alg_tflops) / tf32_peak,
-                                       note="whole validate() timed (SpMM, TF32 split, scorer, merge, metrics); "
-                                            "achieved counts the 3 TF32 MMAs per algorithmic MAC"),
+                                       achieved=(3.0 * alg_tflops if args.dtype == "f32" else alg_tflops) / world,
+                                       peak=tf32_peak, unit="TFLOP/s", per_gpu=True,
+                                       frac=(3.0 * alg_tflops if args.dtype == "f32" else alg_tflops) / world / tf32_peak,
+                                       useful_frac=alg_tflops / world / tf32_peak,
+                                       note="whole validate() timed (SpMM, TF32 split, scorer, merge, metrics), per GPU; "
+                                            "achieved counts the 3 TF32 MMAs per algorithmic MAC (useful_frac counts one); ncu's own "
+                                            "tensor-pipe-active for the kernel alone is in profiles/"),
                          p_at_10=float(res["prec"][1]), ndcg_at_10=float(res["ndcg"][1]), ploss=float(res["ploss"]))
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
@@ -382,10 +413,42 @@ def main():
     e2e_sec = time.perf_counter() - t0
     e2e_sec = dist_util.max_over_ranks(e2e_sec)
     st2 = prob.stats()
-    e2e = dict(value=st2.nnz_traversed / e2e_sec, unit="nnz/s", h2d_bytes_per_step=bytes_model,
+    e2e = dict(value=dist_util.sum_over_ranks(float(st2.nnz_traversed)) / e2e_sec, unit="nnz/s", h2d_bytes_per_step=bytes_model,
                d2h_bytes_per_step=bytes_model, steps=e2e_steps, sec_per_step=e2e_sec / e2e_steps,
                what="per step: ocffm_set_block for every W/H (H2D from pinned fp64 host arrays), ocffm_init_state, "
                     "ocffm_one_epoch, ocffm_get_block for every W/H (D2H into the same pinned arrays)")
+
+    # ---- N > 1: fp64 self-check, N ranks against ONE rank on the same small set ------------------
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        small = synth.generate("C1", seed=args.seed + 7, scale=0.2, test_rows=64)     # identical on every rank
+        sprm = dict(k=16, self_side=True, **HYPER)
+        pn = ocffm.Problem(small, dtype=ocffm.F64, device=local_rank,
+                           comm=(world, rank, dist_util.share_unique_id(ocffm.comm_unique_id)), **sprm)
+        pn.init_model(seed=3)
+        pn.init_state()
+        pn.reset_stats()
+        pn.one_epoch()
+        pn.one_epoch()
+        obj_n, cg_n, val_n = pn.objective(), int(pn.stats().cg_iters), pn.validate(want_topk=False)
+        pn.close()
+        if rank == 0:
+            p1 = ocffm.Problem(small, dtype=ocffm.F64, device=local_rank, **sprm)
+            p1.init_model(seed=3)
+            p1.init_state()
+            p1.reset_stats()
+            p1.one_epoch()
+            p1.one_epoch()
+            obj_1, cg_1, val_1 = p1.objective(), int(p1.stats().cg_iters), p1.validate(want_topk=False)
+            p1.close()
+            parity = dict(what="C1 x0.2, k=16, fp64, 2 outer iterations + validate: N-rank context vs 1-rank context",
+                          objective_1rank=obj_1, objective_nrank=obj_n, cg_1rank=cg_1, cg_nrank=cg_n,
+                          ndcg10_1rank=float(val_1["ndcg"][1]), ndcg10_nrank=float(val_n["ndcg"][1]),
+                          ok=bool(cg_1 == cg_n and abs(obj_1 - obj_n) <= 1e-9 * abs(obj_1)
+                                  and abs(val_1["ndcg"][1] - val_n["ndcg"][1]) <= 1e-9))
+            if not parity["ok"]:
+                print("bench.py: multi-rank parity self-check FAILED: " + json.dumps(parity), file=sys.stderr)
+        dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -403,10 +466,11 @@ def main():
     if rank == 0:
         line = dict(metric="nnz_per_s", value=value, unit="nnz/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic", config=config,
+                    scaling=scaling, vs_baseline=None, dtype=args.dtype, data="synthetic", config=config,
                     sec_per_outer_iteration=sec / args.steps, cg_iters_per_step=st.cg_iters / args.steps,
                     objective=objective, gpu_launches=int(st.kernel_launches), e2e=e2e, roofline=roofline,
-                    cpu_baseline=cpu, eval=eval_info, clocks=sampler.summary(), datagen_s=t_gen)
+                    cpu_baseline=cpu, eval=eval_info, clocks=sampler.summary(), datagen_s=t_gen,
+                    footprint=footprint, multi_rank_parity=parity)
         if int(os.environ.get("OCFFM_PROFILE", "1")) >= 2:      # diagnostic runs only (event timers per phase)
             line["phases_ms_per_step"] = {f: getattr(st, "ms_" + f) / args.steps for f in (
                 "side_grad", "side_cg", "side_update", "cross_grad", "cross_cg", "cross_update")}

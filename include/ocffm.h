@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCFFM_ABI_VERSION 1
+#define OCFFM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define OCFFM_API __attribute__((visibility("default")))
@@ -111,6 +111,14 @@ OCFFM_API int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int whic
  * block, cache_sasb, calc_side, init_y_tilde. */
 OCFFM_API int ocffm_init_state(ocffm_ctx *ctx);
 
+/* Device-side model init: every stored W / H block drawn on the GPU from
+ * U(-s, s), s = 0.1 * qrsqrt(k) as init_mat does (ffm.cpp:3-12, 71-78), by a counter-based generator:
+ * element (row, col) of a block is a pure function of (seed, block, W|H, row, col), so the model is
+ * identical on every rank and for every launch shape, and no model bytes cross PCIe.  It is NOT the
+ * libstdc++ minstd stream of the reference -- use ocffm_set_block with host-drawn values (what the
+ * C++ host layer does by default) when the reference's exact initial model is wanted. */
+OCFFM_API int ocffm_init_model(ocffm_ctx *ctx, uint64_t seed);
+
 /* (lambda, omega, r) sweeps over one uploaded data set (script/grid.sh:186-240 runs a 12 x 3 grid of
  * solves on the same files): change the hyper-parameters of a live context; data, CSC, work lists
  * and hot-feature tables stay resident.  Set the model blocks and call ocffm_init_state again. */
@@ -158,6 +166,11 @@ typedef struct ocffm_stats {
     uint64_t hv_launches;       /* launches of the dominant kernel (hv_cross rows) */
     uint64_t hv_algo_bytes;     /* its algorithmic bytes since reset */
     double hv_ms;               /* its device time since reset (CUDA events, OCFFM_PROFILE=1) */
+    /* ABI 2.  All counters above are THIS RANK's share (sum over ranks = whole job). */
+    uint64_t omega_device_bytes;   /* HBM held by this rank's slices of Omega (both orientations: row pointers,
+                                      column ids, y-tilde, work-item lists) */
+    uint64_t row_gram_bytes;       /* per-row observed Gram buffer (0 when the path is off) */
+    uint64_t row_gram_builds;      /* half solves that built it since reset */
 } ocffm_stats;
 OCFFM_API int ocffm_get_stats(ocffm_ctx *ctx, ocffm_stats *out);
 OCFFM_API int ocffm_reset_stats(ocffm_ctx *ctx);

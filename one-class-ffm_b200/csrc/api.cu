@@ -275,6 +275,7 @@ struct CtxBase {
     virtual void set_block(uint32_t f1, uint32_t f2, int which, const double *data, uint64_t rows) = 0;
     virtual void get_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) = 0;
     virtual void set_hyper(double lambda, double omega, double r) = 0;
+    virtual void init_model(uint64_t seed) = 0;
     virtual void init_state() = 0;
     virtual void solve_block(uint32_t f1, uint32_t f2) = 0;
     virtual void one_epoch() = 0;
@@ -310,6 +311,7 @@ struct Problem final : CtxBase {
     Comm comm;
     uint32_t chunk = 64;
     bool diag_fast = true;      // OCFFM_DIAG_FAST=0 disables the fused same-side CG pass
+    bool notau_allowed = true;  // OCFFM_NOTAU=0: the Hessian row pass always adds w * tau itself
     bool slice_cg = true;       // OCFFM_SLICE_CG=0: always replicate CG vectors across ranks
     // The reference keeps two copies of y-tilde (by user and by item, ffm.cpp:393,400) and adds every
     // update to both with the same arithmetic, so they stay bit-identical.  On one GPU the update
@@ -329,8 +331,13 @@ struct Problem final : CtxBase {
     // Per-row observed Gram for the Hessian passes of cross halves (rows.cu "Mrow").  Default: fp32
     // contexts with kp 16 / 32 (at kp 64 building the Gram costs as much as the gathers it saves;
     // fp64 contexts are the strict-parity mode and keep the reference's summation structure).
-    // OCFFM_MROW=0 off, =1 default rule, =2 also in fp64 contexts; OCFFM_MROW_MIN: pairs per heavy row
+    // Building the blocks costs k*k FMAs per pair (16 gather passes' worth of FLOPs at k = 32), so it
+    // pays only for half solves with many CG iterations: by default (OCFFM_MROW=1, fp32) a half builds
+    // them when its previous solve took >= OCFFM_MROW_ITERS (8) iterations.  OCFFM_MROW=0 never,
+    // =2 always and also in fp64 contexts (tests); OCFFM_MROW_MIN: pairs per heavy row.
     int mrow_mode = 1;
+    int mrow_iters = 8;
+    std::vector<int> last_iters;   // CG iterations of the previous solve of every half (index 2*block + which)
     uint32_t mrow_min = 48;
     size_t mrow_cap_bytes = size_t(3) << 30;
     bool mrow_on = false, mrow_ready = false;
@@ -347,6 +354,7 @@ struct Problem final : CtxBase {
         uint32_t n_hot = 0;
         bool diagonal = false;   // one feature per row, features form a permutation of 0..D-1
         bool identity = false;   // diagonal with idx[i] == i: a rank's rows touch only its own feature slice
+        bool unit_identity = false;   // identity and every value is 1: X is the identity matrix
         uint32_t row0 = 0, row1 = 0;
         CsrView<T> view() const {
             return {rowptr.p, idx.p, val.p, row0, row1, n_hot ? hot_slot.p : nullptr, shadow.p, diagonal, identity};
@@ -359,15 +367,22 @@ struct Problem final : CtxBase {
     struct Omega {
         bool set = false;
         uint64_t rows = 0, nnz = 0, nnz_local = 0;
-        uint32_t n_items = 0, row0 = 0, row1 = 0;
+        uint32_t n_items = 0, n_items_nonempty = 0, row0 = 0, row1 = 0;
         DevBuf<uint32_t> rowptr, idx, wi_row, wi_beg, wi_cnt;
         DevBuf<T> yt;
         DevBuf<uint32_t> mirror_pos;      // position of each entry in the other orientation (mirror_yt)
         bool fresh = true;                // yt holds every update made so far
         std::vector<uint64_t> h_rowptr;   // kept for get_csc / stats
         std::vector<uint32_t> h_idx;
+        // Sharded storage: only this rank's rows live in HBM -- rowptr[row0..row1], and idx / yt for
+        // the nnz [base, base + nnz_local) of those rows.  Kernels keep using GLOBAL row numbers and
+        // nnz positions, so they get the device pointers shifted back by row0 / base.
+        uint64_t base = 0;
+        const uint32_t *rowptr_v() const { return reinterpret_cast<const uint32_t *>(uintptr_t(rowptr.p) - size_t(row0) * 4); }
+        const uint32_t *idx_v() const { return reinterpret_cast<const uint32_t *>(uintptr_t(idx.p) - size_t(base) * 4); }
+        T *yt_v() const { return reinterpret_cast<T *>(uintptr_t(yt.p) - size_t(base) * sizeof(T)); }
         OmegaView<T> view() const {
-            return {wi_row.p, wi_beg.p, wi_cnt.p, n_items, rowptr.p, idx.p, yt.p, row0, row1, nnz_local};
+            return {wi_row.p, wi_beg.p, wi_cnt.p, n_items, rowptr_v(), idx_v(), yt_v(), row0, row1, nnz_local};
         }
         // Per-row observed Gram (rows.cu "Mrow"): the local rows with >= mrow_min pairs are HEAVY --
         // slot s of the Gram buffer belongs to row heavy_rows[s]; hw_* are the build items (<= 1024
@@ -376,8 +391,13 @@ struct Problem final : CtxBase {
         DevBuf<uint32_t> heavy_rows, hw_slot, hw_beg, hw_cnt, lw_row, lw_beg, lw_cnt;
         uint32_t n_heavy = 0, n_multi = 0, n_hw = 0, n_lw = 0;
         uint64_t nnz_heavy = 0;
-        OmegaView<T> light_view() const {
-            return {lw_row.p, lw_beg.p, lw_cnt.p, n_lw, rowptr.p, idx.p, yt.p, row0, row1, nnz_local};
+        uint32_t n_lw_nonempty = 0;
+        OmegaView<T> light_view(bool nonempty_only = false) const {
+            return {lw_row.p, lw_beg.p, lw_cnt.p, nonempty_only ? n_lw_nonempty : n_lw, rowptr_v(), idx_v(), yt_v(), row0,
+                    row1, nnz_local};
+        }
+        OmegaView<T> view_nonempty() const {
+            return {wi_row.p, wi_beg.p, wi_cnt.p, n_items_nonempty, rowptr_v(), idx_v(), yt_v(), row0, row1, nnz_local};
         }
     };
     struct Block {
@@ -441,6 +461,7 @@ struct Problem final : CtxBase {
         XV.resize(fv);
         XT.resize(fu);
         blocks.resize(size_t(f) * (f + 1) / 2);
+        last_iters.assign(blocks.size() * 2, 0);
         for (uint32_t f1 = 0; f1 < f; ++f1)
             for (uint32_t f2 = f1; f2 < f; ++f2) {
                 Block &bk = blocks[bidx(f1, f2)];
@@ -458,9 +479,11 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_HOT_MIN")) hot_min = uint32_t(std::max(0, atoi(e)));
         if (const char *e = getenv("OCFFM_MROW")) mrow_mode = atoi(e);
         if (const char *e = getenv("OCFFM_MROW_MIN")) mrow_min = uint32_t(std::max(1, atoi(e)));
+        if (const char *e = getenv("OCFFM_MROW_ITERS")) mrow_iters = std::max(0, atoi(e));
         if (const char *e = getenv("OCFFM_MROW_CAP_MB")) mrow_cap_bytes = size_t(std::max(1, atoi(e))) << 20;
         mrow_on = mrow_mode != 0 && row_gram_supported(int(kp)) && (std::is_same<T, float>::value || mrow_mode >= 2);
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_NOTAU")) notau_allowed = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_SLICE_CG")) slice_cg = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
@@ -545,7 +568,7 @@ struct Problem final : CtxBase {
             ++occ[idx[t]];
         }
         for (uint64_t d = 0; d < D; ++d) fr[d] = T(occ[d]);
-        F.diagonal = false;
+        F.diagonal = F.identity = F.unit_identity = false;
         if (nnz == rows && D == rows && rows > 0) {
             bool ok = true;
             for (uint64_t i = 0; i < rows && ok; ++i) ok = rowptr[i] == i && occ[idx[i]] == 1;
@@ -553,6 +576,9 @@ struct Problem final : CtxBase {
             bool id = ok;
             for (uint64_t i = 0; i < rows && id; ++i) id = idx[i] == i;
             F.identity = id;
+            bool unit = id;
+            for (uint64_t i = 0; i < rows && unit; ++i) unit = val[i] == 1.0;
+            F.unit_identity = unit;
         }
         F.rowptr.upload(rp, st);
         F.idx.upload(idx, nnz, st);
@@ -592,32 +618,37 @@ struct Problem final : CtxBase {
         OC_REQUIRE(Y.nnz < (1ull << 31), "|Omega| must be below 2^31");
         Y.h_rowptr.assign(rowptr, rowptr + rows + 1);
         Y.h_idx.assign(idx, idx + Y.nnz);
-        std::vector<uint32_t> rp(rows + 1);
-        for (uint64_t i = 0; i <= rows; ++i) rp[i] = uint32_t(rowptr[i]);
         Y.row0 = lo(rows);
         Y.row1 = hi(rows);
+        Y.base = rowptr[Y.row0];
         Y.nnz_local = rowptr[Y.row1] - rowptr[Y.row0];
+        std::vector<uint32_t> rp(Y.row1 - Y.row0 + 1);
+        for (uint64_t i = Y.row0; i <= Y.row1; ++i) rp[i - Y.row0] = uint32_t(rowptr[i]);
+        // work items of the rows with pairs first, then one empty item per row without any: a pass that
+        // has nothing to add for an empty row (hess_cross with notau) launches on the prefix only
         std::vector<uint32_t> wr, wb, wc;
         wr.reserve(Y.row1 - Y.row0 + Y.nnz_local / chunk);
         wb.reserve(wr.capacity());
         wc.reserve(wr.capacity());
         for (uint32_t i = Y.row0; i < Y.row1; ++i) {
             const uint64_t b0 = rowptr[i], e0 = rowptr[i + 1];
-            if (b0 == e0) { wr.push_back(i); wb.push_back(uint32_t(b0)); wc.push_back(0x80000000u); continue; }
             for (uint64_t t = b0; t < e0; t += chunk) {
                 wr.push_back(i);
                 wb.push_back(uint32_t(t));
                 wc.push_back(uint32_t(std::min<uint64_t>(chunk, e0 - t)) | (t == b0 ? 0x80000000u : 0u));
             }
         }
+        Y.n_items_nonempty = uint32_t(wr.size());
+        for (uint32_t i = Y.row0; i < Y.row1; ++i)
+            if (rowptr[i] == rowptr[i + 1]) { wr.push_back(i); wb.push_back(uint32_t(rowptr[i])); wc.push_back(0x80000000u); }
         Y.n_items = uint32_t(wr.size());
         build_heavy_lists(Y, rowptr);
         Y.rowptr.upload(rp, st);
-        Y.idx.upload(idx, Y.nnz, st);
+        Y.idx.upload(idx + Y.base, Y.nnz_local, st);
         Y.wi_row.upload(wr, st);
         Y.wi_beg.upload(wb, st);
         Y.wi_cnt.upload(wc, st);
-        Y.yt.alloc(Y.nnz);
+        Y.yt.alloc(Y.nnz_local);
         Y.yt.zero(st);
         Y.set = true;
         sync();
@@ -662,13 +693,15 @@ struct Problem final : CtxBase {
         for (uint32_t i = Y.row0; i < Y.row1; ++i) {
             const uint64_t b0 = rowptr[i], e0 = rowptr[i + 1];
             if (e0 - b0 >= thr) continue;
-            if (b0 == e0) { lr.push_back(i); lb.push_back(uint32_t(b0)); lc.push_back(0x80000000u); continue; }
             for (uint64_t t = b0; t < e0; t += chunk) {
                 lr.push_back(i);
                 lb.push_back(uint32_t(t));
                 lc.push_back(uint32_t(std::min<uint64_t>(chunk, e0 - t)) | (t == b0 ? 0x80000000u : 0u));
             }
         }
+        Y.n_lw_nonempty = uint32_t(lr.size());
+        for (uint32_t i = Y.row0; i < Y.row1; ++i)
+            if (rowptr[i] == rowptr[i + 1] && thr > 0) { lr.push_back(i); lb.push_back(uint32_t(rowptr[i])); lc.push_back(0x80000000u); }
         Y.n_heavy = uint32_t(hr.size());
         Y.n_multi = uint32_t(multi.size());
         Y.n_hw = uint32_t(hs.size());
@@ -869,6 +902,34 @@ struct Problem final : CtxBase {
         algo_bytes += (uint64_t(Fx) * (m + n) * k * sizeof(T) + (m + n) * sizeof(T)) / uint64_t(comm.nranks);
     }
 
+    // init_pair's init_mat for every stored block, drawn on the device (counter-based, see dense.cu)
+    void init_model(uint64_t seed) override {
+        // the reference's scale 0.1 * qrsqrt(k), qrsqrt being its fast inverse square root (ffm.cpp:3-12)
+        auto qrsqrt = [](double x) {
+            const double xhalf = 0.5 * x;
+            int64_t i;
+            memcpy(&i, &x, sizeof i);
+            i = 0x5fe6eb50c7b537a9ll - (i >> 1);
+            memcpy(&x, &i, sizeof x);
+            x = x * (1.5 - xhalf * x * x);
+            return x;
+        };
+        const double scale = 0.1 * qrsqrt(double(k));
+        for (uint32_t f1 = 0; f1 < f; ++f1)
+            for (uint32_t f2 = f1; f2 < f; ++f2) {
+                Block &bk = blocks[bidx(f1, f2)];
+                if (!bk.exists) continue;
+                OC_REQUIRE(field_of(f1).set && field_of(f2).set, "set every field before ocffm_init_model");
+                const uint64_t rw = field_of(f1).D, rh = field_of(f2).D;
+                bk.W.ensure(rw * kp);
+                bk.H.ensure(rh * kp);
+                init_uniform<T>(bk.W.p, rw, k, kp, seed, 2 * bidx(f1, f2), scale, st);
+                init_uniform<T>(bk.H.p, rh, k, kp, seed, 2 * bidx(f1, f2) + 1, scale, st);
+                bk.has_w = bk.has_h = true;
+            }
+        sync();
+        state_ready = false;
+    }
     void set_hyper(double lambda, double omega, double r) override {
         prm.lambda = lambda;
         prm.omega = omega;
@@ -1045,18 +1106,23 @@ struct Problem final : CtxBase {
     // M_i = sum_{j in Omega_i} q_j q_j^T for the heavy rows of this half (Q1 is fixed during the half
     // solve, ffm.cpp:744-813), so that every CG iteration streams kp x kp numbers per heavy row
     // instead of gathering |Omega_i| rows of Q1
-    void build_mrow(const Half &h) {
+    void build_mrow(const Half &h, bool adaptive = false) {
         mrow_ready = false;
         if (!mrow_on || h.side) return;
+        if (adaptive && mrow_mode < 2 && last_iters[half_id(h)] < mrow_iters) return;
         const Omega &Y = *h.Yown;
         if (!Y.n_heavy) return;
         mrow.ensure(size_t(Y.n_heavy) * kp * kp);
         if (Y.n_multi) OC_CUDA(cudaMemsetAsync(mrow.p, 0, size_t(Y.n_multi) * kp * kp * sizeof(T), st));
-        row_gram<T>(Y.hw_slot.p, Y.hw_beg.p, Y.hw_cnt.p, Y.n_hw, Y.idx.p, h.Q1, h.ldq, mrow.p, int(kp), st);
+        row_gram<T>(Y.hw_slot.p, Y.hw_beg.p, Y.hw_cnt.p, Y.n_hw, Y.idx_v(), h.Q1, h.ldq, mrow.p, int(kp), st);
         algo_bytes += Y.nnz_heavy * 4 + gather_bytes(h.n1 * k * sizeof(T), Y.nnz_heavy, k * sizeof(T)) +
                       uint64_t(Y.n_heavy) * k * k * sizeof(T);
         mrow_ready = true;
         ++mrow_builds;
+    }
+
+    size_t half_id(const Half &h) const {
+        return 2 * size_t(h.bk - blocks.data()) + (h.W1 == h.bk->W.p ? 0 : 1);
     }
 
     size_t hv_event_pair() {
@@ -1089,11 +1155,15 @@ struct Problem final : CtxBase {
                          T(prm.omega), T(prm.r), T(h.n1), Hv.p, kp, gate, dot_out, st);
         } else {
             const size_t o = h.soff() * kp;
+            // identity field with unit values: w * X^T X (V QTQ) = w * V QTQ goes into Hv inside the row
+            // GEMM, the row pass then skips tau and the rows without pairs (every rank must own its rows'
+            // features alone: one rank, or a sliced half)
+            const bool notau = fuse_it >= 0 && notau_allowed && h.X->unit_identity && (!comm.active() || h.sliced);
             if (fuse_it >= 0) {
                 uint64_t lo = 0, hi = h.s1 - h.s0;
                 share_of(h, lo, hi);
                 rowgemm_dir<T>(V.p + o, R.p + o, Hv.p + o, h.freq ? h.freq + h.soff() : nullptr, T(prm.lambda),
-                               lo, hi, qtq_of(h), VQ.p + o, h.s1 - h.s0, kp, fuse_it, sc, st);
+                               lo, hi, qtq_of(h), VQ.p + o, h.s1 - h.s0, kp, fuse_it, sc, notau ? T(prm.omega) : T(0), st);
             } else {
                 rowgemm<T>(V.p + o, kp, kp, qtq_of(h), VQ.p + o, h.s1 - h.s0, kp, gate, st);
             }
@@ -1106,12 +1176,12 @@ struct Problem final : CtxBase {
             if (mrow_ready) {
                 // heavy rows from their Gram blocks, the light rows by gathers
                 hess_heavy_rows<T>(h.Yown->heavy_rows.p, h.Yown->n_heavy, h.X->view(), mrow.p, V.p, VQ.p,
-                                   T(prm.omega), Hv.p, int(kp), gate, dot_out, st);
-                hess_cross_rows<T>(h.Yown->light_view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega),
-                                   Hv.p, kp, gate, dot_out, st);
+                                   T(prm.omega), Hv.p, int(kp), gate, dot_out, notau, st);
+                hess_cross_rows<T>(h.Yown->light_view(notau), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega),
+                                   Hv.p, kp, gate, dot_out, notau, st);
             } else {
-                hess_cross_rows<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p, VQ.p, T(prm.omega), Hv.p,
-                                   kp, gate, dot_out, st);
+                hess_cross_rows<T>(notau ? h.Yown->view_nonempty() : h.Yown->view(), h.X->view(), h.Q1, h.ldq, V.p,
+                                   VQ.p, T(prm.omega), Hv.p, kp, gate, dot_out, notau, st);
             }
             if (profile) OC_CUDA(cudaEventRecord(hv_events[ev].second, st));
         }
@@ -1191,7 +1261,7 @@ struct Problem final : CtxBase {
     int run_cg(const Half &h, bool add_reg) {
         const size_t o = h.soff() * kp;
         const T *fq = h.freq ? h.freq + h.soff() : nullptr;
-        build_mrow(h);
+        build_mrow(h, true);
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
         cg_init<T>(G.p + o, h.W1 + o, fq, add_reg ? T(prm.lambda) : T(0), R.p + o, V.p + o, S.p + o, h.s1 - h.s0,
                    kp, sc, st);
@@ -1218,6 +1288,7 @@ struct Problem final : CtxBase {
         }
         account_hess(h, uint64_t(it));
         cg_iters += uint64_t(it);
+        last_iters[half_id(h)] = it;
         return it;
     }
 
@@ -1413,7 +1484,7 @@ struct Problem final : CtxBase {
         {
             freshen(YU);
             const uint64_t b0 = YU.h_rowptr[YU.row0], e0 = YU.h_rowptr[YU.row1];
-            omega_objective<T>(YU.yt.p + b0, e0 - b0, T(prm.omega), T(prm.r), acc64.p + 4, st);
+            omega_objective<T>(YU.yt_v() + b0, e0 - b0, T(prm.omega), T(prm.r), acc64.p + 4, st);
         }
         comm.allreduce(acc64.p + 4, 1, st);
         for (auto &bk : blocks) {
@@ -1533,8 +1604,19 @@ struct Problem final : CtxBase {
         else if (s == "b") { src = b.p; cnt = n; }
         else if (s == "sa") { src = sa.p; cnt = m; }
         else if (s == "sb") { src = sb.p; cnt = n; }
-        else if (s == "ytilde_csr") { freshen(YU); src = YU.yt.p; cnt = YU.nnz; }
-        else if (s == "ytilde_csc") { freshen(YV); src = YV.yt.p; cnt = YV.nnz; }
+        else if (s == "ytilde_csr" || s == "ytilde_csc") {
+            // a rank holds the cache of its own rows only: the other entries are returned as zeros
+            Omega &Y = s == "ytilde_csr" ? YU : YV;
+            freshen(Y);
+            if (count) *count = Y.nnz;
+            if (!out) return;
+            std::vector<T> hloc(Y.nnz_local);
+            Y.yt.download(hloc.data(), Y.nnz_local, st);
+            sync();
+            std::fill(out, out + Y.nnz, 0.0);
+            for (uint64_t i = 0; i < Y.nnz_local; ++i) out[Y.base + i] = double(hloc[i]);
+            return;
+        }
         else if (s == "popular") { src = popular.p; cnt = n_ranked; }
         else throw Error(OCFFM_E_INVALID, "unknown vector name " + s);
         if (count) *count = cnt;
@@ -1555,12 +1637,9 @@ struct Problem final : CtxBase {
     }
     void get_csc(uint64_t *colptr, uint32_t *rowidx) override {
         OC_REQUIRE(YV.set, "labels not set");
-        std::vector<uint32_t> rp(n + 1), ix(YV.nnz);
-        YV.rowptr.download(rp.data(), n + 1, st);
-        YV.idx.download(ix.data(), YV.nnz, st);
-        sync();
-        for (uint64_t j = 0; j <= n; ++j) colptr[j] = rp[j];
-        std::copy(ix.begin(), ix.end(), rowidx);
+        // the device holds this rank's rows only; the full CSC is kept on the host
+        std::copy(YV.h_rowptr.begin(), YV.h_rowptr.end(), colptr);
+        std::copy(YV.h_idx.begin(), YV.h_idx.end(), rowidx);
     }
     void get_stats(ocffm_stats *out) override {
         drain_hv_events();
@@ -1572,6 +1651,14 @@ struct Problem final : CtxBase {
         out->hv_launches = hv_launches;
         out->hv_algo_bytes = hv_algo_bytes;
         out->hv_ms = hv_ms;
+        auto omega_bytes = [](const Omega &Y) {
+            return (Y.rowptr.n + Y.idx.n + Y.wi_row.n + Y.wi_beg.n + Y.wi_cnt.n + Y.mirror_pos.n + Y.heavy_rows.n +
+                    Y.hw_slot.n + Y.hw_beg.n + Y.hw_cnt.n + Y.lw_row.n + Y.lw_beg.n + Y.lw_cnt.n) * sizeof(uint32_t) +
+                   Y.yt.n * sizeof(T);
+        };
+        out->omega_device_bytes = omega_bytes(YU) + omega_bytes(YV);
+        out->row_gram_bytes = mrow.n * sizeof(T);
+        out->row_gram_builds = mrow_builds;
         // side: grad / cg / update ; cross: grad / cg / update  (OCFFM_PROFILE >= 2)
         out->ms_side_grad = ms[0]; out->ms_side_cg = ms[1]; out->ms_side_update = ms[2];
         out->ms_cross_grad = ms[3]; out->ms_cross_cg = ms[4]; out->ms_cross_update = ms[5];
@@ -1579,7 +1666,7 @@ struct Problem final : CtxBase {
     void reset_stats() override {
         sync();
         drain_hv_events();
-        launches = cg_iters = nnz_trav = algo_bytes = hv_launches = hv_algo_bytes = 0;
+        launches = cg_iters = nnz_trav = algo_bytes = hv_launches = hv_algo_bytes = mrow_builds = 0;
         hv_ms = 0;
         drain_phases();
         for (double &v : ms) v = 0;
@@ -1767,6 +1854,9 @@ int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double 
 }
 int ocffm_set_hyper(ocffm_ctx *ctx, double lambda, double omega, double r) {
     return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.set_hyper(lambda, omega, r); });
+}
+int ocffm_init_model(ocffm_ctx *ctx, uint64_t seed) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.init_model(seed); });
 }
 int ocffm_init_state(ocffm_ctx *ctx) {
     return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.init_state(); });

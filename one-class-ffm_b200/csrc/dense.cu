@@ -3,6 +3,10 @@
 // (T = P~ Gstack, VQTQ = V QTQ), the fused CG vector updates with device-resident fp64 scalars,
 // and small reductions.  SIMT FP32/FP64 with register micro-tiles staged through shared memory;
 // every global scalar is accumulated in fp64 ("Precision vs the 1e-4 tolerance").
+#include <cmath>
+#include <type_traits>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -121,6 +125,10 @@ struct DirFuse {
     T lambda;
     uint64_t sum_lo, sum_hi;   // rows whose |V|^2 this rank accounts for
     double *vv;
+    // Hv is initialised to hv_scale * (V QTQ) instead of 0: on an identity field with unit values the
+    // all-pairs term of hs_cross, w * X_i^T (X_i V QTQ), is exactly w * (V QTQ)_i, so the Hessian row
+    // pass neither reads V QTQ nor visits rows without observed pairs (hv_scale = w; 0 otherwise)
+    T hv_scale;
 };
 
 template <typename T, int KP, int TM, int TN, bool DIR>
@@ -157,7 +165,6 @@ k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restric
                         v.z = rr.z + beta * v.z; v.w = rr.w + beta * v.w;
                         st4(dir.V + off, v);
                     }
-                    st4(dir.Hv + off, zero4<T>());
                     if (m0 + r >= dir.sum_lo && m0 + r < dir.sum_hi) {
                         const T cf = dir.freq ? dir.lambda * dir.freq[m0 + r] : dir.lambda;
                         vv_local += double(cf) * (double(v.x) * v.x + double(v.y) * v.y + double(v.z) * v.z +
@@ -201,6 +208,15 @@ k_rowgemm(const T *__restrict__ A, uint32_t lda, uint32_t Ka, const T *__restric
             for (int j = 0; j < TN; j += 4) {
                 V4<T> v = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
                 st4(C + row * KP + tn * TN + j, v);
+                if (DIR) {
+                    const T hs = dir.hv_scale;
+                    st4(dir.Hv + row * KP + tn * TN + j, V4<T>{hs * v.x, hs * v.y, hs * v.z, hs * v.w});
+                    if (hs != T(0)) {   // this term's share of V . Hv (the row pass no longer sees it)
+                        const V4<T> d4 = ld4(dir.V + row * KP + tn * TN + j);
+                        vv_local += double(hs) * (double(d4.x) * v.x + double(d4.y) * v.y + double(d4.z) * v.z +
+                                                  double(d4.w) * v.w);
+                    }
+                }
             }
         }
     }
@@ -271,6 +287,38 @@ k_pad_from_f64(const double *__restrict__ src, T *__restrict__ dst, uint64_t row
         const uint64_t r = i / ld;
         const uint32_t c = uint32_t(i % ld);
         dst[i] = c < k ? T(src[r * k + c]) : T(0);
+    }
+}
+
+// Counter-based model init: element (row, c) of block-matrix `stream` is
+// scale * (2 u - 1) with u the top 53 bits of a splitmix64 hash of (seed, stream, row * k + c) -- a
+// pure function of the element's coordinates, so any rank / any launch shape draws the same model
+// and nothing crosses PCIe.  Same distribution as init_mat (U(-scale, scale), ffm.cpp:71-78), NOT
+// its libstdc++ minstd stream (the host path keeps that one bit for bit).
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_init_uniform(T *__restrict__ dst, uint64_t rows, uint32_t k, uint32_t ld, uint64_t seed, uint64_t stream,
+               double scale) {
+    pdl_enter();
+    const uint64_t n = rows * ld;
+    const uint64_t key = splitmix64(seed ^ splitmix64(stream));
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / ld;
+        const uint32_t c = uint32_t(i % ld);
+        T v = T(0);
+        if (c < k) {
+            const uint64_t h = splitmix64(key + (r * k + c));
+            const double u = double(h >> 11) * (1.0 / 9007199254740992.0);   // [0, 1)
+            v = T(scale * (2.0 * u - 1.0));
+        }
+        dst[i] = v;
     }
 }
 
@@ -475,10 +523,83 @@ k_omega_objective(const T *__restrict__ yt, uint64_t nnz, T w, T r, double *out6
 // launchers
 // ---------------------------------------------------------------------------------------------
 template <typename T>
+static void gram_stack_simt(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, int kp,
+                            uint32_t row0, uint32_t row1, const T *wvec, double *Out64, double *colsum64,
+                            double *wsum64, int acc_double, cudaStream_t s);
+static void rowgemm_simt_f32(const float *A, uint32_t lda, uint32_t Ka, const float *B, float *C, uint64_t M, int kp,
+                             cudaStream_t s);
+
+// One-time self-check of the tcgen05 kernels against the SIMT ones on a small random problem (the
+// descriptors of the tensor-core path cannot be validated at compile time): a mismatch is reported
+// on stderr and the SIMT kernels keep serving the calls.  1 = verified, 0 = rejected.
+static int tc_selfcheck(uint32_t Kc, cudaStream_t s) {
+    const uint32_t rows = 3000, kp = 32, bcol = (Kc / 32 - 1) * 32;
+    std::vector<float> hA(size_t(rows) * Kc), hw(rows);
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return float(double(x >> 11) * (1.0 / 9007199254740992.0) - 0.5); };
+    for (auto &v : hA) v = rnd();
+    for (auto &v : hw) v = rnd();
+    DevBuf<float> dA, dw, dT1, dT2, dG;
+    DevBuf<double> o1, o2;
+    dA.upload(hA, s);
+    dw.upload(hw, s);
+    const size_t gsz = size_t(Kc) * kp + 2 * kp;
+    o1.alloc(gsz); o2.alloc(gsz);
+    o1.zero(s); o2.zero(s);
+    gram_stack_tc(dA.p, Kc, Kc, bcol, 7, rows, dw.p, o1.p, o1.p + size_t(Kc) * kp, o1.p + size_t(Kc) * kp + kp, s);
+    gram_stack_simt<float>(dA.p, Kc, Kc, dA.p + bcol, Kc, int(kp), 7, rows, dw.p, o2.p, o2.p + size_t(Kc) * kp,
+                           o2.p + size_t(Kc) * kp + kp, 1, s);
+    // row GEMM with the first Kc x 32 block of A as the small operand
+    std::vector<float> hG(hA.begin(), hA.begin() + size_t(Kc) * kp);
+    dG.upload(hG, s);
+    const uint64_t M = rows - 100;
+    dT1.alloc(M * kp); dT2.alloc(M * kp);
+    rowgemm_tc(dA.p + size_t(100) * Kc, Kc, Kc, dG.p, dT1.p, M, s);
+    rowgemm_simt_f32(dA.p + size_t(100) * Kc, Kc, Kc, dG.p, dT2.p, M, int(kp), s);
+    std::vector<double> h1(gsz), h2(gsz);
+    std::vector<float> t1(M * kp), t2(M * kp);
+    o1.download(h1.data(), gsz, s); o2.download(h2.data(), gsz, s);
+    dT1.download(t1.data(), t1.size(), s); dT2.download(t2.data(), t2.size(), s);
+    OC_CUDA(cudaStreamSynchronize(s));
+    double err = 0, scale = 0, terr = 0, tscale = 0;
+    for (size_t i = 0; i < gsz; ++i) { err = std::max(err, std::fabs(h1[i] - h2[i])); scale = std::max(scale, std::fabs(h2[i])); }
+    for (size_t i = 0; i < t1.size(); ++i) { terr = std::max(terr, double(std::fabs(t1[i] - t2[i]))); tscale = std::max(tscale, double(std::fabs(t2[i]))); }
+    const bool ok = err <= 2e-5 * scale && terr <= 2e-5 * tscale && scale > 0 && tscale > 0;
+    if (!ok || getenv("OCFFM_TC_VERBOSE"))
+        fprintf(stderr, "ocffm: tcgen05 Gram / row-GEMM self-check (Kc=%u): gram rel err %.3g, row-GEMM rel err %.3g -> %s\n", Kc,
+                err / std::max(scale, 1e-300), terr / std::max(tscale, 1e-300), ok ? "ok" : "REJECTED, SIMT kernels are used");
+    return ok ? 1 : 0;
+}
+static bool tc_verified(uint32_t Kc, cudaStream_t s) {
+    static int state[2] = {-1, -1};   // Kc = 128, 256
+    int &st = state[Kc == 128 ? 0 : 1];
+    if (st < 0) {
+        st = 0;                        // the check itself must take the explicit paths
+        st = tc_selfcheck(Kc, s);
+    }
+    return st == 1;
+}
+
+template <typename T>
 void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, int kp,
                 uint32_t row0, uint32_t row1, const T *wvec, double *Out64, double *colsum64,
                 double *wsum64, int acc_double, cudaStream_t s) {
     if (row1 <= row0) return;
+    if constexpr (std::is_same<T, float>::value) {
+        // B is a column slice of A (every caller's case): the tensor-core kernel reads A only
+        if (!acc_double && ldb == lda && B >= A && B < A + lda && (B - A) % 32 == 0 && uint32_t(B - A) + uint32_t(kp) <= Kc &&
+            gram_tc_supported(Kc, kp, lda) && tc_verified(Kc, s)) {
+            gram_stack_tc(A, lda, Kc, uint32_t(B - A), row0, row1, wvec, Out64, colsum64, wsum64, s);
+            return;
+        }
+    }
+    gram_stack_simt<T>(A, lda, Kc, B, ldb, kp, row0, row1, wvec, Out64, colsum64, wsum64, acc_double, s);
+}
+
+template <typename T>
+static void gram_stack_simt(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, int kp,
+                            uint32_t row0, uint32_t row1, const T *wvec, double *Out64, double *colsum64,
+                            double *wsum64, int acc_double, cudaStream_t s) {
 #define OC_GRAM(KP, TA, TB)                                                                        \
     if (acc_double)                                                                                \
         launch_gram<T, double, KP, TA, TB>(A, lda, Kc, B, ldb, row0, row1, wvec, Out64, colsum64,  \
@@ -515,12 +636,23 @@ static void rowgemm_impl(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C
 template <typename T>
 void rowgemm(const T *A, uint32_t lda, uint32_t Ka, const T *B, T *C, uint64_t M, int kp, Gate gate,
              cudaStream_t s) {
+    if constexpr (std::is_same<T, float>::value) {
+        // the big ungated product T = P~ Gstack of the gradient: tensor cores (dense_tc)
+        if (gate.it < 0 && rowgemm_tc_supported(Ka, kp, lda, M) && tc_verified(Ka, s)) {
+            rowgemm_tc(A, lda, Ka, B, C, M, s);
+            return;
+        }
+    }
     rowgemm_impl<T>(A, lda, Ka, B, C, M, kp, gate, nullptr, s);
+}
+static void rowgemm_simt_f32(const float *A, uint32_t lda, uint32_t Ka, const float *B, float *C, uint64_t M, int kp,
+                             cudaStream_t s) {
+    rowgemm_impl<float>(A, lda, Ka, B, C, M, kp, kNoGate, nullptr, s);
 }
 template <typename T>
 void rowgemm_dir(T *V, const T *R, T *Hv, const T *freq, T lambda, uint64_t sum_lo, uint64_t sum_hi,
-                 const T *B, T *C, uint64_t M, int kp, int it, SolveScalars *sc, cudaStream_t s) {
-    const DirFuse<T> dir{V, R, Hv, freq, lambda, sum_lo, sum_hi, sc->vpart[it]};
+                 const T *B, T *C, uint64_t M, int kp, int it, SolveScalars *sc, T hv_scale, cudaStream_t s) {
+    const DirFuse<T> dir{V, R, Hv, freq, lambda, sum_lo, sum_hi, sc->vpart[it], hv_scale};
     rowgemm_impl<T>(V, uint32_t(kp), uint32_t(kp), B, C, M, kp, Gate{sc, it}, &dir, s);
 }
 
@@ -534,6 +666,13 @@ template <typename T>
 void pad_from_f64(const double *src, T *dst, uint64_t rows, uint32_t k, uint32_t ld, cudaStream_t s) {
     if (!rows) return;
     OC_LAUNCH((k_pad_from_f64<T>), ew_blocks(rows * ld), kThreads, 0, s, src, dst, rows, k, ld);
+}
+
+template <typename T>
+void init_uniform(T *dst, uint64_t rows, uint32_t k, uint32_t ld, uint64_t seed, uint64_t stream, double scale,
+                  cudaStream_t s) {
+    if (!rows) return;
+    OC_LAUNCH((k_init_uniform<T>), ew_blocks(rows * ld), kThreads, 0, s, dst, rows, k, ld, seed, stream, scale);
 }
 
 template <typename T>
@@ -639,12 +778,14 @@ void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStr
     template void convert_from_f64<T>(const double *, T *, uint64_t, cudaStream_t);                 \
     template void pad_from_f64<T>(const double *, T *, uint64_t, uint32_t, uint32_t, cudaStream_t); \
     template void unpad_to_f64<T>(const T *, uint32_t, double *, uint64_t, uint32_t, cudaStream_t); \
+    template void init_uniform<T>(T *, uint64_t, uint32_t, uint32_t, uint64_t, uint64_t, double,    \
+                                  cudaStream_t);                                                    \
     template void cg_init<T>(T *, const T *, const T *, T, T *, T *, T *, uint64_t, int,            \
                              SolveScalars *, cudaStream_t);                                         \
     template void cg_dir<T>(T *, const T *, T *, uint64_t, int, SolveScalars *, const T *, T, int,  \
                             uint64_t, uint64_t, int, cudaStream_t);                                 \
     template void rowgemm_dir<T>(T *, const T *, T *, const T *, T, uint64_t, uint64_t, const T *,  \
-                                 T *, uint64_t, int, int, SolveScalars *, cudaStream_t);            \
+                                 T *, uint64_t, int, int, SolveScalars *, T, cudaStream_t);         \
     template void cg_reg_dot<T>(T *, const T *, const T *, T, uint64_t, int, int, SolveScalars *,   \
                                 int, cudaStream_t);                                                 \
     template void cg_step<T>(T *, T *, const T *, const T *, uint64_t, int, SolveScalars *,         \

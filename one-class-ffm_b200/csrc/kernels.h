@@ -90,8 +90,8 @@ void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, ui
 // hs_cross row pass (ffm.cpp:715-738): phi = X_i V, tau = X_i (V QTQ), ka = sum_j (phi.q_j) q_j
 template <typename T>
 void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
-                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out,
-                     cudaStream_t s);   // dot_out (optional) += V . Hv, as sum over work items of phi . z
+                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, int notau,
+                     cudaStream_t s);   // notau: the w * tau term is already in Hv (rowgemm_dir hv_scale)   // dot_out (optional) += V . Hv, as sum over work items of phi . z
 
 // ysum[row] = sum of y-tilde over the row (first half of gd_side's z_i, ffm.cpp:577-580)
 template <typename T>
@@ -141,7 +141,7 @@ void row_gram(const uint32_t *it_slot, const uint32_t *it_beg, const uint32_t *i
               const uint32_t *yidx, const T *Q1, uint32_t ldq, T *M, int kp, cudaStream_t s);
 template <typename T>
 void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView<T> &X, const T *M, const T *V,
-                     const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, cudaStream_t s);
+                     const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, int notau, cudaStream_t s);
 
 // ---- dense.cu --------------------------------------------------------------------------------
 // Out64[Kc x kp] += A[rows x Kc]^T B[rows x kp]; colsum64[0:kp] += B^T 1 ; wsum64[0:kp] += B^T wvec
@@ -150,6 +150,16 @@ template <typename T>
 void gram_stack(const T *A, uint32_t lda, uint32_t Kc, const T *B, uint32_t ldb, int kp,
                 uint32_t row0, uint32_t row1, const T *wvec, double *Out64, double *colsum64,
                 double *wsum64, int acc_double, cudaStream_t s);
+
+// gram_tc.cu (fp32, kp = 32, Kc = 128 / 256, B = columns [bcol, bcol + kp) of A): the same contraction on
+// tcgen05 (TMA-fed MN-major operands, 3xTF32, fp32 TMEM accumulate flushed to fp64 every 512 rows)
+bool gram_tc_supported(uint32_t Kc, int kp, uint32_t lda);
+void gram_stack_tc(const float *A, uint32_t lda, uint32_t Kc, uint32_t bcol, uint32_t row0, uint32_t row1,
+                   const float *wvec, double *Out64, double *colsum64, double *wsum64, cudaStream_t s);
+
+// row GEMM C[M x 32] = A[M x Ka] B[Ka x 32] on tcgen05 (Ka = 128 / 256, fp32 in / out, 3xTF32)
+bool rowgemm_tc_supported(uint32_t Ka, int kp, uint32_t lda, uint64_t M);
+void rowgemm_tc(const float *A, uint32_t lda, uint32_t Ka, const float *B, float *C, uint64_t M, cudaStream_t s);
 
 // C[M x kp] = A[M x Ka] B[Ka x kp]   (T = P~ Gstack, ffm.cpp:663-670; VQTQ = V QTQ, ffm.cpp:799)
 template <typename T>
@@ -163,6 +173,10 @@ template <typename T>
 void pad_from_f64(const double *src, T *dst, uint64_t rows, uint32_t k, uint32_t ld, cudaStream_t s);
 template <typename T>
 void unpad_to_f64(const T *src, uint32_t ld, double *dst, uint64_t rows, uint32_t k, cudaStream_t s);
+// dst[rows x ld] (zero padded beyond k) = U(-scale, scale), a counter-based function of (seed, stream, row, col)
+template <typename T>
+void init_uniform(T *dst, uint64_t rows, uint32_t k, uint32_t ld, uint64_t seed, uint64_t stream, double scale,
+                  cudaStream_t s);
 
 // G += lambda * (freq ? freq[row] : 1) * W ; R = -G ; V = R ; S = 0 ; sc->r2[0] += ||G||^2
 template <typename T>
@@ -177,7 +191,8 @@ void cg_dir(T *V, const T *R, T *Hv, uint64_t n, int it, SolveScalars *sc, const
 // cross halves: the same direction update folded into VQ = V * QTQ (one pass over V)
 template <typename T>
 void rowgemm_dir(T *V, const T *R, T *Hv, const T *freq, T lambda, uint64_t sum_lo, uint64_t sum_hi,
-                 const T *B, T *C, uint64_t M, int kp, int it, SolveScalars *sc, cudaStream_t s);
+                 const T *B, T *C, uint64_t M, int kp, int it, SolveScalars *sc, T hv_scale, cudaStream_t s);
+// hv_scale: Hv = hv_scale * C instead of 0 (see DirFuse::hv_scale; then hess_cross_rows runs with notau)
 // Hv += lambda * (freq ? freq[row] : 1) * V ; sc->vHv[it] += V . Hv
 template <typename T>
 void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, int it,

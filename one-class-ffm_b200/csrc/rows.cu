@@ -176,7 +176,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
              const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate,
-             double *__restrict__ dot_out) {
+             double *__restrict__ dot_out, int notau) {
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
     constexpr int U = G < 8 ? G : 8;   // gathers kept in flight per lane
@@ -188,7 +188,7 @@ k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
         const uint32_t mask = group_mask<G>();
         const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
         const uint32_t cnt = c & 0x7fffffffu;
-        const bool first = (c >> 31) != 0;
+        const bool first = (c >> 31) != 0 && !notau;   // notau: w * tau is already in Hv
         const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
         uint32_t j = lg < cnt ? Y.idx[beg + lg] : 0u;
         V4<T> phi = zero4<T>(), tau = zero4<T>();
@@ -584,7 +584,7 @@ template <typename T, int KP>
 __global__ void __launch_bounds__(kThreads)
 k_hess_heavy(const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy, CsrView<T> X,
              const T *__restrict__ M, const T *__restrict__ V, const T *__restrict__ VQ, T w,
-             T *__restrict__ Hv, Gate gate, double *__restrict__ dot_out) {
+             T *__restrict__ Hv, Gate gate, double *__restrict__ dot_out, int notau) {
     pdl_enter();
     constexpr int G = KP / 4, NG = 32 / G, STEPS = KP / NG;
     static_assert(STEPS <= G, "every component of z needs an owner lane");
@@ -604,7 +604,7 @@ k_hess_heavy(const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy, CsrView<
             const T v = X.val[t];
             fma4(phi4, v, ldg4(V + off + lg * 4));
             phi_o += v * __ldg(V + off + zi);
-            tau_o += v * __ldg(VQ + off + zi);
+            if (!notau) tau_o += v * __ldg(VQ + off + zi);
         }
         const T *Mi = M + size_t(slot) * KP * KP + size_t(g * STEPS) * KP + lg * 4;
         T d[STEPS];
@@ -671,11 +671,11 @@ void grad_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, ui
 
 template <typename T>
 void hess_cross_rows(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq,
-                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out,
+                     const T *V, const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, int notau,
                      cudaStream_t s) {
     if (!Y.n_items) return;
     OC_DISPATCH_G(kp, OC_LAUNCH((k_hess_cross<T, G>), blocks_for(Y.n_items, G), kThreads, 0, s, Y, X,
-                                Q1, ldq, V, VQ, w, Hv, gate, dot_out));
+                                Q1, ldq, V, VQ, w, Hv, gate, dot_out, notau));
 }
 
 template <typename T>
@@ -771,13 +771,13 @@ void row_gram(const uint32_t *it_slot, const uint32_t *it_beg, const uint32_t *i
 
 template <typename T>
 void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView<T> &X, const T *M, const T *V,
-                     const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, cudaStream_t s) {
+                     const T *VQ, T w, T *Hv, int kp, Gate gate, double *dot_out, int notau, cudaStream_t s) {
     if (!n_heavy) return;
     const unsigned blocks = unsigned((uint64_t(n_heavy) * 32 + kThreads - 1) / kThreads);
     if (kp == 32)
-        OC_LAUNCH((k_hess_heavy<T, 32>), blocks, kThreads, 0, s, heavy_rows, n_heavy, X, M, V, VQ, w, Hv, gate, dot_out);
+        OC_LAUNCH((k_hess_heavy<T, 32>), blocks, kThreads, 0, s, heavy_rows, n_heavy, X, M, V, VQ, w, Hv, gate, dot_out, notau);
     else if (kp == 16)
-        OC_LAUNCH((k_hess_heavy<T, 16>), blocks, kThreads, 0, s, heavy_rows, n_heavy, X, M, V, VQ, w, Hv, gate, dot_out);
+        OC_LAUNCH((k_hess_heavy<T, 16>), blocks, kThreads, 0, s, heavy_rows, n_heavy, X, M, V, VQ, w, Hv, gate, dot_out, notau);
     else
         throw Error(-6, "per-row Gram needs a padded latent dimension of 16 or 32");
 }
@@ -790,7 +790,7 @@ void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView
                                      const T *, const T *, const T *, const T *, T, T, T *, int,   \
                                      cudaStream_t);                                                \
     template void hess_cross_rows<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, \
-                                     const T *, const T *, T, T *, int, Gate, double *,            \
+                                     const T *, const T *, T, T *, int, Gate, double *, int,       \
                                      cudaStream_t);                                                \
     template void ytilde_rowsum<T>(const OmegaView<T> &, T *, int, cudaStream_t);                  \
     template void side_rows<T>(int, const OmegaView<T> &, const CsrView<T> &, const T *, const T *, \
@@ -807,7 +807,7 @@ void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView
     template void row_gram<T>(const uint32_t *, const uint32_t *, const uint32_t *, uint32_t,      \
                               const uint32_t *, const T *, uint32_t, T *, int, cudaStream_t);      \
     template void hess_heavy_rows<T>(const uint32_t *, uint32_t, const CsrView<T> &, const T *,    \
-                                     const T *, const T *, T, T *, int, Gate, double *, cudaStream_t);
+                                     const T *, const T *, T, T *, int, Gate, double *, int, cudaStream_t);
 
 OC_INSTANTIATE(float)
 OC_INSTANTIATE(double)

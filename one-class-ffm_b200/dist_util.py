@@ -53,6 +53,18 @@ def max_over_ranks(value: float) -> float:
     return float(t.item())
 
 
+def sum_over_ranks(value: float) -> float:
+    import torch
+    import torch.distributed as dist
+    _, world, _ = env_rank()
+    if world == 1 or not dist.is_initialized():
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def barrier():
     import torch.distributed as dist
     _, world, _ = env_rank()

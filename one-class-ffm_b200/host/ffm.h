@@ -58,6 +58,7 @@ public:
     bool self_side, freq = false;
     int dtype = OCFFM_F32;   // device arithmetic; OCFFM_F64 reproduces the reference to ~1e-10
     int device = -1;         // CUDA ordinal, -1 = current
+    unsigned long gpu_init_seed = 0;   // != 0: draw the initial model on the GPU (ocffm_init_model), not with init_mat's RNG
     Parameter() : omega(0.1), lambda(1e-5), r(-1), nr_pass(20), k(4), nr_threads(1), self_side(true) {}
 };
 

@@ -513,9 +513,25 @@ void ImpProblem::prepare_shapes() {
 
 void ImpProblem::init() {
     prepare_shapes();
-    if (W.empty()) init_model_random();   // a model loaded by load_binary_model() is kept
+    const bool device_init = param->gpu_init_seed != 0 && W.empty();
+    if (W.empty() && !device_init) init_model_random();   // a model loaded by load_binary_model() is kept
     attach();
-    push_model();
+    if (device_init) {
+        // counter-based init on the GPU: no host RNG pass, no model upload
+        check(ocffm_init_model(ctx, param->gpu_init_seed), "ocffm_init_model");
+        const ImpInt nr_blocks = f * (f + 1) / 2;
+        W.assign(nr_blocks, Vec());
+        H.assign(nr_blocks, Vec());
+        for (ImpInt f1 = 0; f1 < f; f1++)
+            for (ImpInt f2 = f1; f2 < f; f2++) {
+                if (!block_exists(f1, f2)) continue;
+                W[index_of(f1, f2)].assign(block_rows(f1) * k, 0);
+                H[index_of(f1, f2)].assign(block_rows(f2) * k, 0);
+            }
+        host_model_stale = true;   // the writers pull the blocks from the device on demand
+    } else {
+        push_model();
+    }
     check(ocffm_init_state(ctx), "ocffm_init_state");
 }
 

@@ -79,6 +79,8 @@ const char *kUsage =
     "--ns: drop the same-side blocks\n"
     "--freq: enable freq-aware lambda\n"
     "--f64: solve in fp64 on the device (default fp32 storage, fp64 scalars)\n"
+    "--gpu-init <seed>: draw the initial model on the GPU (counter-based generator, same distribution as the\n"
+    "    reference's init_mat but not its random stream; default: the reference's host RNG, bit for bit)\n"
     "--device <n>: CUDA device ordinal\n"
     "--load <path>: start from a binary model (save_binary_model layout)\n"
     "--save-binary <path>: also write the binary model\n"
@@ -118,6 +120,10 @@ Option parse_option(int argc, char **argv) {
         } else if (a == "--ns") p.self_side = false;
         else if (a == "--freq") p.freq = true;
         else if (a == "--f64") p.dtype = OCFFM_F64;
+        else if (a == "--gpu-init") {
+            p.gpu_init_seed = strtoul(numeric_value(argc, argv, i, "need to specify a seed after --gpu-init", "--gpu-init should be followed by a number"), nullptr, 10);
+            if (p.gpu_init_seed == 0) throw invalid_argument("--gpu-init needs a non-zero seed");
+        }
         else if (a == "--predict-only") opt.predict_only = true;
         else if (a == "--cache") opt.cache = true;
         else break;   // first non-flag token ends option parsing

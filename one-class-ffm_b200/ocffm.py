@@ -37,13 +37,14 @@ class Stats(C.Structure):
                 ("algo_bytes", C.c_uint64), ("ms_side_grad", C.c_double), ("ms_side_cg", C.c_double),
                 ("ms_side_update", C.c_double), ("ms_cross_grad", C.c_double), ("ms_cross_cg", C.c_double),
                 ("ms_cross_update", C.c_double), ("hv_launches", C.c_uint64), ("hv_algo_bytes", C.c_uint64),
-                ("hv_ms", C.c_double)]
+                ("hv_ms", C.c_double), ("omega_device_bytes", C.c_uint64), ("row_gram_bytes", C.c_uint64),
+                ("row_gram_builds", C.c_uint64)]
 
 
 EXPORTS = [
     "ocffm_abi_version", "ocffm_last_error", "ocffm_device_count", "ocffm_create", "ocffm_destroy",
     "ocffm_comm_unique_id", "ocffm_shard_range", "ocffm_comm_init", "ocffm_set_field", "ocffm_set_labels",
-    "ocffm_set_test_labels", "ocffm_set_hyper", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
+    "ocffm_set_test_labels", "ocffm_set_hyper", "ocffm_init_model", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
     "ocffm_solve_block", "ocffm_one_epoch", "ocffm_grad", "ocffm_hess_vec", "ocffm_cg",
     "ocffm_objective", "ocffm_validate", "ocffm_get_vec", "ocffm_get_embed", "ocffm_get_csc",
     "ocffm_get_stats", "ocffm_reset_stats", "ocffm_synchronize", "ocffm_stream",
@@ -77,6 +78,7 @@ def lib():
         L.ocffm_set_block.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
         L.ocffm_get_block.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
         L.ocffm_init_state.argtypes = [vp]
+        L.ocffm_init_model.argtypes = [vp, C.c_uint64]
         L.ocffm_set_hyper.argtypes = [vp, C.c_double, C.c_double, C.c_double]
         L.ocffm_solve_block.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.ocffm_one_epoch.argtypes = [vp]
@@ -239,6 +241,10 @@ class Problem:
                 out[(f1, f2, which)] = rng.uniform(-s, s, size=(self.block_rows(f1, f2, which), self.k))
                 self.set_block(f1, f2, which, out[(f1, f2, which)])
         return out
+
+    def init_model_device(self, seed: int = 1):
+        """Counter-based init on the GPU (ocffm_init_model): same distribution as init_mat, no PCIe."""
+        self._ck(self.L.ocffm_init_model(self.h, seed))
 
     def init_state(self):
         self._ck(self.L.ocffm_init_state(self.h))

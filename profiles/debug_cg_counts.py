@@ -10,11 +10,12 @@ k = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 ds = synth.generate(shape, seed=3, test_rows=300, cold_rows=5)
 prm = dict(k=k, lam=4.0, omega=2.0 ** -7, r=-1.0, self_side=True, freq=False)
 o = pyoracle.Oracle(ds, **prm)
-p = ocffm.Problem(ds, dtype=ocffm.F64, **prm)
+p = ocffm.Problem(ds, dtype=ocffm.F32 if os.environ.get("DBG_F32") else ocffm.F64, **prm)
 rng = np.random.default_rng(11)
 for f1, f2 in o.blocks():
     for which in "WH":
-        w = rng.uniform(-0.05, 0.05, size=(o.block_rows(f1, f2, which), k))
+        sc = float(os.environ.get("DBG_SCALE", 0.1 / np.sqrt(k)))
+        w = rng.uniform(-sc, sc, size=(o.block_rows(f1, f2, which), k))
         o.set_block(f1, f2, which, w); p.set_block(f1, f2, which, w)
 o.init_state(); p.init_state()
 fu = ds.users.f

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_library_is_built_and_loads():
     ocffm.build()
     L = ocffm.lib()
-    assert L.ocffm_abi_version() == 1
+    assert L.ocffm_abi_version() == 2
 
 
 def test_every_declared_symbol_is_exported():

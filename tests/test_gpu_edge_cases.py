@@ -128,3 +128,41 @@ def test_hyper_parameter_sweep_reuses_resident_data():
         assert abs(p.objective() - fresh.objective()) <= 1e-11 * abs(fresh.objective())
         assert np.allclose(p.validate()["ndcg"], fresh.validate()["ndcg"], rtol=1e-9)
         fresh.close()
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_device_side_model_init(dt):
+    """ocffm_init_model: counter-based draw on the GPU -- reproducible from the seed,
+    independent of the context, different per block / per W|H / per seed, uniform in
+    (-0.1 qrsqrt(k), 0.1 qrsqrt(k)) like init_mat (ffm.cpp:3-12, 71-78); a solve from it matches the
+    oracle fed with the same numbers."""
+    synth = importlib.import_module("synth")
+    dtype, tol = (ocffm.F64, 1e-9) if dt == "f64" else (ocffm.F32, 2e-4)
+    ds = synth.generate("C1", seed=5, scale=0.1, test_rows=30)
+    prm = dict(k=16, lam=4.0, omega=2.0 ** -7, r=-1.0, self_side=True, freq=False)
+    p = ocffm.Problem(ds, dtype=dtype, **prm)
+    p.init_model_device(seed=7)
+    blocks = {(f1, f2, w): p.get_block(f1, f2, w) for f1, f2 in p.blocks() for w in "WH"}
+    q = ocffm.Problem(ds, dtype=dtype, **prm)
+    q.init_model_device(seed=7)
+    for key, v in blocks.items():
+        assert np.array_equal(q.get_block(*key), v), key          # same seed -> same model, any context
+    q.init_model_device(seed=8)
+    bound = 0.1 * 0.24957703567795358                            # 0.1 * qrsqrt(16) (SURVEY 7, probe value)
+    allv = np.concatenate([v.ravel() for v in blocks.values()])
+    assert np.all(np.abs(allv) <= bound * (1 + 1e-6)) and np.max(np.abs(allv)) > 0.98 * bound
+    assert abs(float(np.mean(allv))) < 4 * bound / np.sqrt(3 * allv.size)         # mean of U(-b, b) within 4 sigma
+    assert abs(float(np.var(allv)) - bound * bound / 3) < 0.02 * bound * bound / 3
+    keys = sorted(blocks)
+    for a_, b_ in zip(keys, keys[1:]):
+        n = min(blocks[a_].size, blocks[b_].size)
+        assert not np.array_equal(blocks[a_].ravel()[:n], blocks[b_].ravel()[:n])  # streams differ
+    assert not np.array_equal(q.get_block(*keys[0]), blocks[keys[0]])              # seeds differ
+    o = pyoracle.Oracle(ds, **prm)
+    for key, v in blocks.items():
+        o.set_block(*key, v)
+    o.init_state()
+    p.init_state()
+    o.one_epoch()
+    p.one_epoch()
+    assert abs(p.objective() - o.func()) <= 10 * tol * abs(o.func())

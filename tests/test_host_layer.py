@@ -65,6 +65,10 @@ def test_cli_usage_and_argument_errors():
     # grid runner flags
     r = run(["--grid-l", "1,x", "a", "b"])
     assert r.returncode == 1 and "--grid-l should be followed by a comma-separated list of numbers" in r.stderr
+    r = run(["--gpu-init"])
+    assert r.returncode == 1 and "need to specify a seed after --gpu-init" in r.stderr
+    r = run(["--gpu-init", "0", "a", "b"])
+    assert r.returncode == 1 and "non-zero seed" in r.stderr
     r = run(["--grid-w"])
     assert r.returncode == 1 and "need to specify a list after --grid-w" in r.stderr
     base = os.path.join(GOLDEN, "tiny", "tiny")

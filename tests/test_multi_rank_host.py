@@ -37,9 +37,10 @@ def _worker(rank, world, port, out):
     dist_util.init("gloo")
     uid = dist_util.share_unique_id(lambda: bytes(range(128)))
     slowest = dist_util.max_over_ranks(10.0 + rank)
+    total = dist_util.sum_over_ranks(100.0 * (rank + 1))      # per-rank counters -> job totals (bench.py)
     dist_util.barrier()
     lo, hi = ocffm.shard_range(1001, world, rank)
-    out.put((rank, uid, slowest, lo, hi))
+    out.put((rank, uid, slowest, lo, hi, total))
     dist.destroy_process_group()
 
 
@@ -58,4 +59,5 @@ def test_gloo_world2_plumbing():
         assert p.exitcode == 0
     assert all(r[1] == bytes(range(128)) for r in res)      # every rank received rank 0's id
     assert all(r[2] == 11.0 for r in res)                   # max over ranks
+    assert all(r[5] == 300.0 for r in res)                  # sum over ranks
     assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 500, 500, 1001)

@@ -141,3 +141,22 @@ def test_binary_model_save_load_predict_round_trip(case):
         hdr = np.fromfile(mb, dtype=np.uint32, count=4)
         want_hdr, _ = read_model(mt)
         assert list(hdr) == want_hdr[:4]
+
+
+def test_gpu_init_flag_trains_and_is_reproducible():
+    """--gpu-init <seed>: the initial model is drawn on the device (ocffm_init_model); two runs with the
+    same seed print the same log and write the same model, another seed gives another model."""
+    gdir = os.path.join(GOLDEN, "tiny")
+    flags = open(os.path.join(gdir, "cli_flags.txt")).read().split()
+    base = os.path.join(gdir, "tiny")
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for i, seed in enumerate(["11", "11", "12"]):
+            model = os.path.join(tmp, f"m{i}.txt")
+            r = subprocess.run([TRAIN] + flags + ["--f64", "--gpu-init", seed, "-c", "1", "-p", base + ".te", "-o", model,
+                                                   base + ".item", base + ".tr"], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            outs.append((r.stdout, open(model).read()))
+    assert outs[0] == outs[1]
+    assert outs[0][1] != outs[2][1]
+    assert len(outs[0][0].strip().split("\n")) == 3          # header + iterations 10 and 20
