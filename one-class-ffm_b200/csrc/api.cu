@@ -311,7 +311,10 @@ struct Problem final : CtxBase {
     Comm comm;
     uint32_t chunk = 64;
     bool diag_fast = true;      // OCFFM_DIAG_FAST=0 disables the fused same-side CG pass
-    bool notau_allowed = true;  // OCFFM_NOTAU=0: the Hessian row pass always adds w * tau itself
+    // OCFFM_NOTAU=1: on unit identity fields w * (V QTQ) is written into Hv by the row GEMM and the Hessian
+    // row pass skips tau and the rows without pairs.  Measured (round 2): C2 18.62 -> 18.44 ms per outer
+    // iteration, but C4 226 -> 233 ms (the GEMM epilogue re-reads V for the V.Hv share) -- off by default.
+    bool notau_allowed = false;
     bool slice_cg = true;       // OCFFM_SLICE_CG=0: always replicate CG vectors across ranks
     // The reference keeps two copies of y-tilde (by user and by item, ffm.cpp:393,400) and adds every
     // update to both with the same arithmetic, so they stay bit-identical.  On one GPU the update
