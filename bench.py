@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N > 1: weak = one block of the shape's users per GPU, strong = the fixed shape sharded")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the 1-rank vs N-rank fp64 self-check")
@@ -300,7 +301,14 @@ def main():
     dtype = ocffm.F32 if args.dtype == "f32" else ocffm.F64
     os.environ.setdefault("OCFFM_PROFILE", "1")     # CUDA events around every hv_cross launch
     prob = ocffm.Problem(ds, k=k, dtype=dtype, device=local_rank, self_side=not args.ns, comm=comm, **HYPER)
-    model = prob.init_model(seed=args.seed)
+    # the multi-million-row shapes draw their model on the GPU (ocffm_init_model: no 10 GB host copy per
+    # rank); the others with numpy on the host, as round 1 did
+    big_model = shape in ("C3", "C4")
+    if big_model:
+        prob.init_model_device(seed=args.seed)
+        model = {(f1, f2, w): None for f1, f2 in prob.blocks() for w in "WH"}
+    else:
+        model = prob.init_model(seed=args.seed)
     prob.init_state()
     stream = torch.cuda.ExternalStream(prob.stream(), device=torch.device("cuda", local_rank))
 
@@ -355,6 +363,20 @@ def main():
                     whole_epoch_frac_per_gpu=(st.algo_bytes / 1e9) / sec / pk["hbm_gbs"],
                     whole_epoch_gbs_all_gpus=(algo_total / 1e9) / sec,
                     row_gram_builds=int(st.row_gram_builds), row_gram_bytes=int(st.row_gram_bytes))
+    if st.cg_kernel_launches:
+        # cross halves solved by the persistent CG kernel: the Hessian row pass is a phase of that kernel,
+        # so the roofline is the fused kernel's -- ALL its algorithmic bytes (per iteration: the hs_cross
+        # formula of SURVEY 8(a) A7 + 7 D k s of CG vector traffic, A8) over its event-timed duration
+        ck_gbs = (st.cg_kernel_algo_bytes / 1e9) / (st.cg_kernel_ms / 1e3)
+        roofline.update(
+            kernel="k_cg_cross_persist (one cooperative launch per cross half solve; per CG iteration: direction + V*QTQ, "
+                   "hs_cross row pass (gathers), step; grid-wide barriers in between)",
+            achieved=ck_gbs, frac=ck_gbs / pk["hbm_gbs"], launches=int(st.cg_kernel_launches),
+            avg_launch_ms=st.cg_kernel_ms / st.cg_kernel_launches,
+            avg_cg_iteration_ms=st.cg_kernel_ms / max(1, st.cg_kernel_iters), cg_iterations=int(st.cg_kernel_iters),
+            share_of_step=st.cg_kernel_ms / ms if ms > 0 else None,
+            algo_bytes_per_launch=st.cg_kernel_algo_bytes / st.cg_kernel_launches,
+            separate_hessian_passes=dict(launches=int(st.hv_launches), ms=st.hv_ms, gbs=hv_gbs))
     free_b, total_b = torch.cuda.mem_get_info(local_rank)
     footprint = dict(omega_device_bytes=int(st.omega_device_bytes), hbm_used_bytes=int(total_b - free_b),
                      note="per rank (rank 0): Omega slices = row pointers, column ids, y-tilde and work-item lists of both orientations")
@@ -392,31 +414,41 @@ def main():
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
     e2e_steps = min(args.steps, 3)
-    # the model lives in PINNED host memory (the library DMAs straight from / into it)
-    host_model = {}
-    for key in model:
-        rows = prob.block_rows(*key)
-        buf = torch.empty((rows, k), dtype=torch.float64, pin_memory=True).numpy()
-        host_model[key] = prob.get_block(*key, out=buf)
-    bytes_model = int(sum(v.nbytes for v in host_model.values()))
-    barrier()
-    prob.reset_stats()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    bytes_model = int(sum(prob.block_rows(*key) * k * 8 for key in model))
+    # every rank keeps a pinned fp64 copy of the whole model for this leg: skipped when that would pin
+    # more than 32 GB of host memory on the node (C4 at N = 8: 8 x 12 GB)
+    if args.no_e2e or bytes_model * world > (32 << 30):
+        e2e = dict(value=None, unit="nnz/s", h2d_bytes_per_step=bytes_model, d2h_bytes_per_step=bytes_model, steps=0,
+                   what=f"skipped: {bytes_model / 2**30:.1f} GiB of fp64 model per rank x {world} ranks of pinned host memory")
+    else:
+        # the model lives in PINNED host memory (the library DMAs straight from / into it)
+        host_model = {}
+        for key in model:
+            rows = prob.block_rows(*key)
+            buf = torch.empty((rows, k), dtype=torch.float64, pin_memory=True).numpy()
+            host_model[key] = prob.get_block(*key, out=buf)
         for key, w in host_model.items():
-            prob.set_block(key[0], key[1], key[2], w)      # H2D
-        prob.init_state()
-        prob.one_epoch()
+            prob.mirror_block(key[0], key[1], key[2], w)   # one_epoch() keeps these host copies current
+        barrier()
+        prob.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for key, w in host_model.items():
+                prob.set_block(key[0], key[1], key[2], w)      # H2D of the whole model
+            prob.init_state()
+            prob.one_epoch()                                   # D2H of every block inside (second stream)
+        prob.synchronize()
+        e2e_sec = time.perf_counter() - t0
+        e2e_sec = dist_util.max_over_ranks(e2e_sec)
+        st2 = prob.stats()
+        e2e = dict(value=dist_util.sum_over_ranks(float(st2.nnz_traversed)) / e2e_sec, unit="nnz/s",
+                   h2d_bytes_per_step=bytes_model, d2h_bytes_per_step=bytes_model, steps=e2e_steps,
+                   sec_per_step=e2e_sec / e2e_steps,
+                   what="per step: ocffm_set_block for every W/H (H2D from pinned fp64 host arrays), ocffm_init_state, "
+                        "ocffm_one_epoch with every W/H registered as a host mirror (ocffm_mirror_block): each block is "
+                        "copied back (D2H, fp64) into the same pinned arrays right after its solve, on a second stream")
         for key in host_model:
-            prob.get_block(*key, out=host_model[key])      # D2H
-    prob.synchronize()
-    e2e_sec = time.perf_counter() - t0
-    e2e_sec = dist_util.max_over_ranks(e2e_sec)
-    st2 = prob.stats()
-    e2e = dict(value=dist_util.sum_over_ranks(float(st2.nnz_traversed)) / e2e_sec, unit="nnz/s", h2d_bytes_per_step=bytes_model,
-               d2h_bytes_per_step=bytes_model, steps=e2e_steps, sec_per_step=e2e_sec / e2e_steps,
-               what="per step: ocffm_set_block for every W/H (H2D from pinned fp64 host arrays), ocffm_init_state, "
-                    "ocffm_one_epoch, ocffm_get_block for every W/H (D2H into the same pinned arrays)")
+            prob.mirror_block(key[0], key[1], key[2], None)
 
     # ---- N > 1: fp64 self-check, N ranks against ONE rank on the same small set ------------------
     parity = None

@@ -111,6 +111,15 @@ OCFFM_API int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int whic
  * block, cache_sasb, calc_side, init_y_tilde. */
 OCFFM_API int ocffm_init_state(ocffm_ctx *ctx);
 
+/* Host mirrors.  The reference keeps W / H in host memory (ffm.h:107) and one_epoch() updates them in
+ * place; a caller that needs that after EVERY outer iteration registers a PINNED fp64 [rows x k]
+ * buffer per block half.  While a mirror is registered, ocffm_one_epoch converts and copies the block
+ * into it on a second stream right after the block's solve of the iteration -- overlapped with the
+ * remaining block solves -- and returns once every mirror is current.  pinned == NULL unregisters.
+ * (ocffm_get_block remains the one-off, serial download.) */
+OCFFM_API int ocffm_mirror_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double *pinned,
+                                 uint64_t rows);
+
 /* Device-side model init: every stored W / H block drawn on the GPU from
  * U(-s, s), s = 0.1 * qrsqrt(k) as init_mat does (ffm.cpp:3-12, 71-78), by a counter-based generator:
  * element (row, col) of a block is a pure function of (seed, block, W|H, row, col), so the model is
@@ -171,6 +180,11 @@ typedef struct ocffm_stats {
                                       column ids, y-tilde, work-item lists) */
     uint64_t row_gram_bytes;       /* per-row observed Gram buffer (0 when the path is off) */
     uint64_t row_gram_builds;      /* half solves that built it since reset */
+    /* cross halves solved by the persistent CG kernel (one cooperative launch per half solve: direction +
+     * V QTQ, hs_cross row pass and step of every iteration), timed with CUDA events under OCFFM_PROFILE=1 */
+    double cg_kernel_ms;
+    uint64_t cg_kernel_algo_bytes; /* algorithmic bytes of those solves (Hessian passes + CG vector passes) */
+    uint64_t cg_kernel_launches, cg_kernel_iters;
 } ocffm_stats;
 OCFFM_API int ocffm_get_stats(ocffm_ctx *ctx, ocffm_stats *out);
 OCFFM_API int ocffm_reset_stats(ocffm_ctx *ctx);

@@ -274,6 +274,7 @@ struct CtxBase {
                                  const uint64_t *nnx) = 0;
     virtual void set_block(uint32_t f1, uint32_t f2, int which, const double *data, uint64_t rows) = 0;
     virtual void get_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) = 0;
+    virtual void mirror_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) = 0;
     virtual void set_hyper(double lambda, double omega, double r) = 0;
     virtual void init_model(uint64_t seed) = 0;
     virtual void init_state() = 0;
@@ -408,6 +409,7 @@ struct Problem final : CtxBase {
         uint32_t f1 = 0, f2 = 0;
         int pair = -1;
         DevBuf<T> W, H, P, Q;
+        double *mirW = nullptr, *mirH = nullptr;   // registered pinned host mirrors (ocffm_mirror_block)
     };
 
     std::vector<Field> XU, XV, XT;
@@ -437,6 +439,11 @@ struct Problem final : CtxBase {
     size_t h_stage_n = 0;
     DevBuf<double> d_stage;
     cudaEvent_t cg_ev[24], g2_ev;
+    // host mirrors: blocks are streamed out on a second stream while the rest of the iteration runs
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t solved_ev = nullptr;
+    DevBuf<double> mir_stage;
+    uint64_t mirrors = 0, mirrored_bytes = 0;
 
     // stats
     uint64_t launches = 0, cg_iters = 0, nnz_trav = 0, algo_bytes = 0, hv_launches = 0,
@@ -487,6 +494,7 @@ struct Problem final : CtxBase {
         mrow_on = mrow_mode != 0 && row_gram_supported(int(kp)) && (std::is_same<T, float>::value || mrow_mode >= 2);
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_NOTAU")) notau_allowed = atoi(e) != 0;
+        if (const char *e = getenv("OCFFM_PERSIST_CG")) { persist_mode = atoi(e); persist_on = persist_mode != 0; }
         if (const char *e = getenv("OCFFM_SLICE_CG")) slice_cg = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PROFILE")) { profile_level = atoi(e); profile = profile_level != 0; }
         a.alloc(m); b.alloc(n); sa.alloc(m); sb.alloc(n);
@@ -504,11 +512,15 @@ struct Problem final : CtxBase {
         if (st) cudaStreamSynchronize(st);
         comm.close_peers();   // imports first, then this rank's own buffers are freed
         for (auto &e : hv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto &e : cgk_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto &e : cg_ev) cudaEventDestroy(e);
         cudaEventDestroy(g2_ev);
         if (sc) cudaFree(sc);
         if (h_scal) cudaFreeHost(h_scal);
+        if (h_iters) cudaFreeHost(h_iters);
         if (h_stage) cudaFreeHost(h_stage);
+        if (copy_st) { cudaStreamSynchronize(copy_st); cudaStreamDestroy(copy_st); }
+        if (solved_ev) cudaEventDestroy(solved_ev);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -517,6 +529,7 @@ struct Problem final : CtxBase {
     void sync() {
         OC_CUDA(cudaStreamSynchronize(st));
         comm.check_peer();
+        drain_pending();
     }
     void bind() {
         OC_CUDA(cudaSetDevice(device));
@@ -890,6 +903,39 @@ struct Problem final : CtxBase {
         download_unpadded(block_mat(bk, which).p, kp, data, rows);
     }
 
+    // The reference keeps W / H in host memory and one_epoch() updates them in place.  A caller that
+    // needs the host copy current after every outer iteration registers pinned fp64 mirrors; one_epoch
+    // then converts + copies each block on a second stream right after the block's solve, overlapped
+    // with the remaining block solves, instead of a serial download of the whole model afterwards.
+    void mirror_block(uint32_t f1, uint32_t f2, int which, double *data, uint64_t rows) override {
+        OC_REQUIRE(which == 'W' || which == 'H', "which must be 'W' or 'H'");
+        Block &bk = block(f1, f2);
+        OC_REQUIRE(rows == block_rows(bk, which), "rows must equal Ds of the block's field");
+        OC_REQUIRE(!data || is_pinned(data), "a host mirror must be pinned (page-locked) memory");
+        double *&slot = which == 'W' ? bk.mirW : bk.mirH;
+        if (!slot && data) ++mirrors;
+        if (slot && !data) --mirrors;
+        slot = data;
+        if (data && !copy_st) {
+            OC_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+            OC_CUDA(cudaEventCreateWithFlags(&solved_ev, cudaEventDisableTiming));
+        }
+    }
+    void stream_out(Block &bk) {
+        if (!bk.mirW && !bk.mirH) return;
+        OC_CUDA(cudaEventRecord(solved_ev, st));
+        OC_CUDA(cudaStreamWaitEvent(copy_st, solved_ev, 0));
+        for (int which : {'W', 'H'}) {
+            double *dst = which == 'W' ? bk.mirW : bk.mirH;
+            if (!dst) continue;
+            const uint64_t rows = block_rows(bk, which);
+            mir_stage.ensure(rows * k);   // grows only on the first iteration (sized by the largest block)
+            unpad_to_f64<T>(block_mat(bk, which).p, kp, mir_stage.p, rows, k, copy_st);
+            OC_CUDA(cudaMemcpyAsync(dst, mir_stage.p, rows * k * sizeof(double), cudaMemcpyDeviceToHost, copy_st));
+            mirrored_bytes += rows * k * sizeof(double);
+        }
+    }
+
     // ------------------------------------------------------------------------------------------
     // cache_sasb, ffm.cpp:514-535: sa = Pc colsum(Qc), sb = Qc colsum(Pc)
     void cache_sasb() {
@@ -1261,10 +1307,80 @@ struct Problem final : CtxBase {
         OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaEventRecord(cg_ev[it], st));
     }
+    // ---- persistent CG (cg_side_persist): iteration counts are read back at the next sync ----------
+    bool persist_on = true;            // OCFFM_PERSIST_CG=0: per-iteration kernels + host stop test everywhere
+    struct PendingCg { Half h; int slot; int ev; };
+    // OCFFM_PROFILE: events around every persistent CG kernel of a cross half
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> cgk_events;
+    size_t cgk_events_used = 0;
+    double cgk_ms = 0;
+    uint64_t cgk_bytes = 0, cgk_launches = 0, cgk_iters = 0;
+    std::vector<PendingCg> pending;
+    unsigned *h_iters = nullptr;       // pinned
+    static constexpr int kIterSlots = 1024;
+    int last_drained_iters = 0;
+    void drain_pending() {             // the stream is idle: every slot has landed
+        for (const PendingCg &pc : pending) {
+            const int it = int(h_iters[pc.slot]);
+            const uint64_t before = algo_bytes;
+            account_hess(pc.h, uint64_t(it));
+            if (pc.ev >= 0) {   // a profiled cross solve: the fused kernel's time and ALL its algorithmic bytes
+                float t = 0;
+                if (cudaEventElapsedTime(&t, cgk_events[pc.ev].first, cgk_events[pc.ev].second) == cudaSuccess) cgk_ms += t;
+                cgk_bytes += algo_bytes - before;
+                cgk_launches += 1;
+                cgk_iters += uint64_t(it);
+            }
+            cg_iters += uint64_t(it);
+            last_iters[half_id(pc.h)] = it;
+            last_drained_iters = it;
+        }
+        pending.clear();
+        cgk_events_used = 0;
+    }
+    int persist_mode = 2;              // OCFFM_PERSIST_CG: 0 off, 1 same-side halves only, 2 cross halves too
+    bool persist_eligible(const Half &h) const {
+        if (!persist_on || comm.active() || h.X->n_hot) return false;
+        if (h.side) return true;
+        return persist_mode >= 2 && !mrow_ready && cg_cross_persist_supported(int(kp), sizeof(T));
+    }
+    void run_cg_persist(const Half &h, bool add_reg) {
+        OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
+        cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, st);
+        int ev = -1;
+        if (profile && !h.side) {
+            if (cgk_events_used == cgk_events.size()) {
+                cudaEvent_t e0, e1;
+                OC_CUDA(cudaEventCreate(&e0));
+                OC_CUDA(cudaEventCreate(&e1));
+                cgk_events.emplace_back(e0, e1);
+            }
+            ev = int(cgk_events_used++);
+            OC_CUDA(cudaEventRecord(cgk_events[ev].first, st));
+        }
+        if (h.side)
+            cg_side_persist<T>(h.Yown->view(), h.X->view(), h.Q1, V.p, R.p, S.p, Hv.p, h.freq, T(prm.lambda),
+                               T(prm.omega), T(h.n1), h.D, int(kp), h.X->diagonal && diag_fast, sc, 20, 9e-2, st);
+        else
+            cg_cross_persist<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, qtq_of(h), V.p, R.p, S.p, Hv.p, VQ.p, h.freq,
+                                T(prm.lambda), T(prm.omega), h.D, int(kp), sc, 20, 9e-2, st);
+        if (ev >= 0) OC_CUDA(cudaEventRecord(cgk_events[ev].second, st));
+        if (!h_iters) OC_CUDA(cudaMallocHost(&h_iters, kIterSlots * sizeof(unsigned)));
+        if (int(pending.size()) >= kIterSlots) sync();   // (never inside one outer iteration: 2 x blocks << 1024)
+        const int slot = int(pending.size());
+        OC_CUDA(cudaMemcpyAsync(h_iters + slot, &sc->counter[2], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        pending.push_back(PendingCg{h, slot, ev});
+    }
+
     int run_cg(const Half &h, bool add_reg) {
+        if (!h.side) build_mrow(h, true);   // decides mrow_ready before the path is chosen
+        if (persist_eligible(h)) {
+            run_cg_persist(h, add_reg);
+            return -1;   // the count arrives with the next sync (drain_pending)
+        }
         const size_t o = h.soff() * kp;
         const T *fq = h.freq ? h.freq + h.soff() : nullptr;
-        build_mrow(h, true);
+        if (h.side) mrow_ready = false;
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
         cg_init<T>(G.p + o, h.W1 + o, fq, add_reg ? T(prm.lambda) : T(0), R.p + o, V.p + o, S.p + o, h.s1 - h.s0,
                    kp, sc, st);
@@ -1394,16 +1510,27 @@ struct Problem final : CtxBase {
     }
     void one_epoch() override {
         OC_REQUIRE(state_ready, "call ocffm_init_state first");
+        if (mirrors) {   // the staging buffer must not be re-allocated while the copy stream uses it
+            uint64_t mx = 0;
+            for (auto &bk : blocks)
+                if (bk.exists) mx = std::max(mx, std::max(block_rows(bk, 'W'), block_rows(bk, 'H')));
+            mir_stage.ensure(mx * k);
+        }
+        auto solve = [&](uint32_t f1, uint32_t f2) {
+            solve_block(f1, f2);
+            if (mirrors) stream_out(blocks[bidx(f1, f2)]);
+        };
         if (prm.self_side) {
             for (uint32_t f1 = 0; f1 < fu; ++f1)
-                for (uint32_t f2 = f1; f2 < fu; ++f2) solve_block(f1, f2);
+                for (uint32_t f2 = f1; f2 < fu; ++f2) solve(f1, f2);
             for (uint32_t f1 = fu; f1 < f; ++f1)
-                for (uint32_t f2 = f1; f2 < f; ++f2) solve_block(f1, f2);
+                for (uint32_t f2 = f1; f2 < f; ++f2) solve(f1, f2);
         }
         for (uint32_t f1 = 0; f1 < fu; ++f1)
-            for (uint32_t f2 = fu; f2 < f; ++f2) solve_block(f1, f2);
+            for (uint32_t f2 = fu; f2 < f; ++f2) solve(f1, f2);
         if (prm.self_side) cache_sasb();
         sync();
+        if (mirrors) OC_CUDA(cudaStreamSynchronize(copy_st));   // every registered mirror is current on return
         if (profile) { drain_hv_events(); drain_phases(); }
     }
 
@@ -1446,7 +1573,8 @@ struct Problem final : CtxBase {
         upload_padded(G, Gin, h.D);
         if (!h.side) prepare_cross(h);
         const uint64_t before = cg_iters;
-        const int it = run_cg(h, false);
+        int it = run_cg(h, false);
+        if (it < 0) { sync(); it = last_drained_iters; }
         if (h.sliced) comm.allgather_rows(S.p, h.D, kp, st);
         cg_iters = before;
         if (iters) *iters = it;
@@ -1662,6 +1790,10 @@ struct Problem final : CtxBase {
         out->omega_device_bytes = omega_bytes(YU) + omega_bytes(YV);
         out->row_gram_bytes = mrow.n * sizeof(T);
         out->row_gram_builds = mrow_builds;
+        out->cg_kernel_ms = cgk_ms;
+        out->cg_kernel_algo_bytes = cgk_bytes;
+        out->cg_kernel_launches = cgk_launches;
+        out->cg_kernel_iters = cgk_iters;
         // side: grad / cg / update ; cross: grad / cg / update  (OCFFM_PROFILE >= 2)
         out->ms_side_grad = ms[0]; out->ms_side_cg = ms[1]; out->ms_side_update = ms[2];
         out->ms_cross_grad = ms[3]; out->ms_cross_cg = ms[4]; out->ms_cross_update = ms[5];
@@ -1670,6 +1802,8 @@ struct Problem final : CtxBase {
         sync();
         drain_hv_events();
         launches = cg_iters = nnz_trav = algo_bytes = hv_launches = hv_algo_bytes = mrow_builds = 0;
+        cgk_ms = 0;
+        cgk_bytes = cgk_launches = cgk_iters = 0;
         hv_ms = 0;
         drain_phases();
         for (double &v : ms) v = 0;
@@ -1854,6 +1988,9 @@ int ocffm_get_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double 
         OC_REQUIRE(data, "null array");
         c.get_block(f1, f2, which, data, rows);
     });
+}
+int ocffm_mirror_block(ocffm_ctx *ctx, uint32_t f1, uint32_t f2, int which, double *pinned, uint64_t rows) {
+    return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.mirror_block(f1, f2, which, pinned, rows); });
 }
 int ocffm_set_hyper(ocffm_ctx *ctx, double lambda, double omega, double r) {
     return with_ctx(ctx, [&](ocffm::CtxBase &c) { c.set_hyper(lambda, omega, r); });

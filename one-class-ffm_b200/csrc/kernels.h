@@ -111,6 +111,20 @@ template <typename T>
 void side_diag_iter(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, const T *R, T *Hv,
                     const T *freq, T lambda, T w, T n1, int kp, int it, SolveScalars *sc, cudaStream_t s);
 
+// The whole CG solve of a same-side half in one cooperative launch (single rank, field without hot
+// features): S, R, V as left by cg_init; on return sc->r2[1..it], sc->vHv[0..it-1] and sc->counter[2] = it.
+template <typename T>
+void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, T *R, T *S, T *Hv, const T *freq,
+                     T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
+                     cudaStream_t s);
+
+// ... and of a cross half (QTQ [kp x kp] of this pair; kp <= 32, or 64 in fp32)
+bool cg_cross_persist_supported(int kp, size_t elem);
+template <typename T>
+void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
+                      T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
+                      int max_cg, double eps, cudaStream_t s);
+
 // y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
 template <typename T>
 void sddmm_add(const OmegaView<T> &Y, const T *Uown, uint32_t ldu, const T *Vo, uint32_t ldv,

@@ -49,6 +49,21 @@ __device__ __forceinline__ T *scatter_row(const CsrView<T> &X, T *Out, uint32_t 
     return Out + size_t(idx) * kp;
 }
 
+// L2-only loads (ld.global.cg) for data written earlier in the same kernel by other CTAs
+template <typename T>
+__device__ __forceinline__ V4<T> ldcg4(const T *p);
+template <>
+__device__ __forceinline__ V4<float> ldcg4<float>(const float *p) {
+    const float4 v = __ldcg(reinterpret_cast<const float4 *>(p));
+    return {v.x, v.y, v.z, v.w};
+}
+template <>
+__device__ __forceinline__ V4<double> ldcg4<double>(const double *p) {
+    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+    return {a.x, a.y, b.x, b.y};
+}
+
 template <typename T>
 __device__ __forceinline__ V4<T> scale4(const V4<T> &v, T s) {
     return {v.x * s, v.y * s, v.z * s, v.w * s};
@@ -172,70 +187,79 @@ k_grad_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ld
         red4(scatter_row(X, Gout, X.identity ? row : X.idx[t], kp) + lg * 4, scale4(pk, X.val[t]));
 }
 
+// One work item of the hs_cross row pass (ffm.cpp:715-738): phi = X_i V, tau = X_i (V QTQ) on the
+// row's first item, ka = sum_j (phi . q_j) q_j over the item's pairs, Hv += X_i^T ((1-w) ka + w tau);
+// returns this lane's share of V . (X^T z) = phi . z.  COH: V / VQ were written earlier in the SAME
+// kernel by other CTAs (persistent CG) and must be read past the non-coherent L1.
+template <typename T, int G, bool COH>
+__device__ __forceinline__ T hess_cross_item(const OmegaView<T> &Y, const CsrView<T> &X, const T *__restrict__ Q1,
+                                             uint32_t ldq, const T *V, const T *VQ, T w, T *Hv, uint32_t item,
+                                             int notau) {
+    constexpr uint32_t kp = 4 * G;
+    constexpr int U = G < 8 ? G : 8;   // gathers kept in flight per lane
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
+    const uint32_t cnt = c & 0x7fffffffu;
+    const bool first = (c >> 31) != 0 && !notau;   // notau: w * tau is already in Hv
+    const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
+    uint32_t j = lg < cnt ? Y.idx[beg + lg] : 0u;
+    V4<T> phi = zero4<T>(), tau = zero4<T>();
+    for (uint32_t t = xb; t < xe; ++t) {
+        const size_t off = size_t(X.identity ? row : X.idx[t]) * kp + lg * 4;
+        const T v = X.val[t];
+        fma4(phi, v, COH ? ldcg4(V + off) : ldg4(V + off));
+        if (first) fma4(tau, v, COH ? ldcg4(VQ + off) : ldg4(VQ + off));
+    }
+    V4<T> ka = zero4<T>();
+    const T *qbase = Q1 + lg * 4;
+    for (uint32_t base = 0; base < cnt; base += G) {
+        const uint32_t nb = base + G + lg;
+        const uint32_t jn = nb < cnt ? Y.idx[beg + nb] : 0u;   // next batch of column ids
+#pragma unroll
+        for (int l0 = 0; l0 < G; l0 += U) {
+            if (base + l0 >= cnt) break;   // entries past cnt: row 0, zero coefficient (see k_grad_cross)
+            V4<T> q[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
+            if constexpr (G == 8 && sizeof(T) == 4) {   // fp64 would spill: it keeps the plain sums
+                T d[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d[u] = dot4(phi, q[u]);
+                T mine = reduce_scatter8(d, lg, mask);   // phi . q of gathered row lg
+                if (base + lg >= cnt) mine = T(0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) fma4(ka, __shfl_sync(mask, mine, u, 8), q[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    T sdot = gsum<G>(dot4(phi, q[u]), mask);
+                    if (base + l0 + u >= cnt) sdot = T(0);
+                    fma4(ka, sdot, q[u]);
+                }
+            }
+        }
+        j = jn;
+    }
+    const T omw = T(1) - w;
+    V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
+               omw * ka.w + w * tau.w};
+    for (uint32_t t = xb; t < xe; ++t)
+        red4(scatter_row(X, Hv, X.identity ? row : X.idx[t], kp) + lg * 4, scale4(z, X.val[t]));
+    return dot4(phi, z);
+}
+
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_hess_cross(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq,
              const T *__restrict__ V, const T *__restrict__ VQ, T w, T *__restrict__ Hv, Gate gate,
              double *__restrict__ dot_out, int notau) {
     pdl_enter();
-    constexpr uint32_t kp = 4 * G;
-    constexpr int U = G < 8 ? G : 8;   // gathers kept in flight per lane
     if (!gate_open(gate)) return;
     const uint64_t item = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     T vhv = T(0);   // this lane's share of V . (X^T z) = (X_i V) . z
-    if (item < Y.n_items) {
-        const uint32_t lg = threadIdx.x % G;
-        const uint32_t mask = group_mask<G>();
-        const uint32_t row = Y.wi_row[item], beg = Y.wi_beg[item], c = Y.wi_cnt[item];
-        const uint32_t cnt = c & 0x7fffffffu;
-        const bool first = (c >> 31) != 0 && !notau;   // notau: w * tau is already in Hv
-        const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
-        uint32_t j = lg < cnt ? Y.idx[beg + lg] : 0u;
-        V4<T> phi = zero4<T>(), tau = zero4<T>();
-        for (uint32_t t = xb; t < xe; ++t) {
-            const size_t off = size_t(X.identity ? row : X.idx[t]) * kp + lg * 4;
-            const T v = X.val[t];
-            fma4(phi, v, ldg4(V + off));
-            if (first) fma4(tau, v, ldg4(VQ + off));
-        }
-        V4<T> ka = zero4<T>();
-        const T *qbase = Q1 + lg * 4;
-        for (uint32_t base = 0; base < cnt; base += G) {
-            const uint32_t nb = base + G + lg;
-            const uint32_t jn = nb < cnt ? Y.idx[beg + nb] : 0u;   // next batch of column ids
-#pragma unroll
-            for (int l0 = 0; l0 < G; l0 += U) {
-                if (base + l0 >= cnt) break;   // entries past cnt: row 0, zero coefficient (see k_grad_cross)
-                V4<T> q[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    q[u] = ldg4(qbase + size_t(__shfl_sync(mask, j, l0 + u, G)) * ldq);
-                if constexpr (G == 8 && sizeof(T) == 4) {   // fp64 would spill: it keeps the plain sums
-                    T d[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) d[u] = dot4(phi, q[u]);
-                    T mine = reduce_scatter8(d, lg, mask);   // phi . q of gathered row lg
-                    if (base + lg >= cnt) mine = T(0);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) fma4(ka, __shfl_sync(mask, mine, u, 8), q[u]);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        T sdot = gsum<G>(dot4(phi, q[u]), mask);
-                        if (base + l0 + u >= cnt) sdot = T(0);
-                        fma4(ka, sdot, q[u]);
-                    }
-                }
-            }
-            j = jn;
-        }
-        const T omw = T(1) - w;
-        V4<T> z = {omw * ka.x + w * tau.x, omw * ka.y + w * tau.y, omw * ka.z + w * tau.z,
-                   omw * ka.w + w * tau.w};
-        vhv = dot4(phi, z);
-        for (uint32_t t = xb; t < xe; ++t)
-            red4(scatter_row(X, Hv, X.identity ? row : X.idx[t], kp) + lg * 4, scale4(z, X.val[t]));
-    }
+    if (item < Y.n_items) vhv = hess_cross_item<T, G, false>(Y, X, Q1, ldq, V, VQ, w, Hv, uint32_t(item), notau);
     if (dot_out) warp_add_slot(double(vhv), dot_out, kDotSlots);
 }
 
@@ -626,6 +650,249 @@ k_hess_heavy(const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy, CsrView<
     if (dot_out) warp_add_slot(double(vhv), dot_out, kDotSlots);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// A whole CG solve of a same-side half (cg, ffm.cpp:744-813 with hs_side, ffm.cpp:594-628) in ONE
+// cooperative launch.  The per-iteration kernels of a same-side half are tiny (a few microseconds of
+// work on L2-resident vectors), so the 3-4 launches per iteration plus the host's event wait
+// dominated; here the CTAs stay resident, iterate with grid-wide barriers and evaluate the stop test
+// (g2 * 0.09 < r2, at most 20 iterations) themselves -- the host enqueues one kernel per half solve
+// and never waits inside an outer iteration.
+//   general field : [V = R + beta V, Hv = 0, reg share of V.Hv] | [rows: Hv += X^T q d (q . X V), data
+//                   share of V.Hv] | [alpha; S += alpha V; R -= alpha (Hv + lambda c V); ||R||^2]
+//   diagonal field: [rows: direction, Hv (regulariser included), V.Hv -- row-local, no atomics] |
+//                   [alpha; S += alpha V; R -= alpha Hv; ||R||^2]
+// Every grid-wide sum is "per-CTA partial -> barrier -> every CTA adds the partials in the same
+// order", so all CTAs take bit-identical stop decisions.  Vectors written inside the kernel are read
+// back with ld.global.cg (L1 is not coherent across SMs).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPersistMaxBlocks = 592;   // two partial arrays inside SolveScalars::partials
+
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += 1;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * gridDim.x;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+// sum of the per-CTA partials, same order in every CTA (valid in all threads)
+__device__ __forceinline__ double sum_partials(const double *part) {
+    __shared__ double bc;
+    double v = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(part + i);
+    v = block_sum(v);
+    if (threadIdx.x == 0) bc = v;
+    __syncthreads();
+    v = bc;
+    __syncthreads();
+    return v;
+}
+
+template <typename T, int G, bool DIAG>
+__global__ void __launch_bounds__(kThreads)
+k_cg_side_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__restrict__ V, T *__restrict__ R,
+                  T *__restrict__ S, T *__restrict__ Hv, const T *__restrict__ freq, T lambda, T w, T n1,
+                  uint64_t D, SolveScalars *sc, int max_cg, double eps) {
+    pdl_enter();
+    constexpr uint32_t kp = 4 * G;
+    double *part_a = sc->partials, *part_b = sc->partials + kPersistMaxBlocks;
+    unsigned *counter = &sc->counter[1];
+    unsigned epoch = 0;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t nvec = D * (kp / 4);
+    const uint32_t rows = X.row1 - X.row0;
+    const double g2 = sc->r2[0];
+    double r2 = g2, r2_prev = 0;   // carried in registers: L1 is not coherent with block 0's stores to sc->r2[]
+    int it = 0;
+    while (g2 * eps < r2 && it < max_cg) {
+        const T beta = it > 0 ? T(r2 / r2_prev) : T(0);
+        double local = 0;
+        if (!DIAG) {
+            for (uint64_t i = tid; i < nvec; i += nthreads) {
+                V4<T> v = ldcg4(V + i * 4);
+                if (it > 0) {
+                    const V4<T> r = ldcg4(R + i * 4);
+                    v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
+                    st4(V + i * 4, v);
+                }
+                st4(Hv + i * 4, zero4<T>());
+                const T c = freq ? lambda * freq[i / (kp / 4)] : lambda;
+                local += double(c) * (double(v.x) * v.x + double(v.y) * v.y + double(v.z) * v.z + double(v.w) * v.w);
+            }
+            grid_barrier(counter, epoch);
+            for (uint64_t g = tid / G; g < rows; g += nthreads / G) {
+                const uint32_t row = X.row0 + uint32_t(g);
+                const T cnt = T(Y.rowptr[row + 1] - Y.rowptr[row]);
+                const V4<T> q = ldg4(Q1 + size_t(row) * kp + lg * 4);
+                const uint32_t xb = X.rowptr[row], xe = X.rowptr[row + 1];
+                T acc = T(0);
+                for (uint32_t t = xb; t < xe; ++t)
+                    acc += X.val[t] * dot4(q, ldcg4(V + size_t(X.idx[t]) * kp + lg * 4));
+                const T sdot = gsum<G>(acc, mask);
+                const T z = sdot * ((T(1) - w) * cnt + w * n1);
+                if (lg == 0) local += double(sdot) * double(z);
+                for (uint32_t t = xb; t < xe; ++t)
+                    red4(Hv + size_t(X.idx[t]) * kp + lg * 4, scale4(q, X.val[t] * z));
+            }
+        } else {
+            for (uint64_t g = tid / G; g < rows; g += nthreads / G) {
+                const uint32_t row = X.row0 + uint32_t(g);
+                const uint32_t f = X.idx[row];
+                const T x = X.val[row];
+                const size_t off = size_t(f) * kp + lg * 4;
+                V4<T> v = ldcg4(V + off);
+                if (it > 0) {
+                    const V4<T> r = ldcg4(R + off);
+                    v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
+                    st4(V + off, v);
+                }
+                const V4<T> q = ldg4(Q1 + size_t(row) * kp + lg * 4);
+                const T cnt = T(Y.rowptr[row + 1] - Y.rowptr[row]);
+                const T z = gsum<G>(dot4(q, v), mask) * x * ((T(1) - w) * cnt + w * n1) * x;
+                const T c = freq ? lambda * freq[f] : lambda;
+                const V4<T> h = {c * v.x + q.x * z, c * v.y + q.y * z, c * v.z + q.z * z, c * v.w + q.w * z};
+                st4(Hv + off, h);
+                local += double(v.x) * h.x + double(v.y) * h.y + double(v.z) * h.z + double(v.w) * h.w;
+            }
+        }
+        local = block_sum(local);
+        if (threadIdx.x == 0) part_a[blockIdx.x] = local;
+        grid_barrier(counter, epoch);
+        const double vhv = sum_partials(part_a);
+        const T alpha = T(r2 / vhv);
+        local = 0;
+        for (uint64_t i = tid; i < nvec; i += nthreads) {
+            const V4<T> v = ldcg4(V + i * 4);
+            V4<T> h = ldcg4(Hv + i * 4);
+            if (!DIAG) {   // Hv holds the data term only: add lambda c_f V here (ffm.cpp:788-790)
+                const T c = freq ? lambda * freq[i / (kp / 4)] : lambda;
+                h.x += c * v.x; h.y += c * v.y; h.z += c * v.z; h.w += c * v.w;
+            }
+            V4<T> sv = ldcg4(S + i * 4), r = ldcg4(R + i * 4);
+            sv.x += alpha * v.x; sv.y += alpha * v.y; sv.z += alpha * v.z; sv.w += alpha * v.w;
+            r.x -= alpha * h.x; r.y -= alpha * h.y; r.z -= alpha * h.z; r.w -= alpha * h.w;
+            st4(S + i * 4, sv);
+            st4(R + i * 4, r);
+            local += double(r.x) * r.x + double(r.y) * r.y + double(r.z) * r.z + double(r.w) * r.w;
+        }
+        local = block_sum(local);
+        if (threadIdx.x == 0) part_b[blockIdx.x] = local;
+        grid_barrier(counter, epoch);
+        const double r2n = sum_partials(part_b);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            sc->vHv[it] = vhv;
+            sc->r2[it + 1] = r2n;
+        }
+        r2_prev = r2;
+        r2 = r2n;
+        ++it;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->counter[2] = unsigned(it);
+}
+
+
+// The same for a CROSS half (cg with hs_cross, ffm.cpp:706-742, 744-813): per iteration
+//   [per feature row: V = R + beta V, Hv = 0, VQ = V QTQ (QTQ in shared memory), reg share of V.Hv] |
+//   [hs_cross work items: gathers of Q1 rows, Hv += X^T z, data share of V.Hv] | [step, ||R||^2]
+// with three grid-wide barriers.  kp <= 64 (QTQ must fit the static shared memory).
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
+k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq, const T *__restrict__ QTQ,
+                   T *__restrict__ V, T *__restrict__ R, T *__restrict__ S, T *__restrict__ Hv, T *__restrict__ VQ,
+                   const T *__restrict__ freq, T lambda, T w, uint64_t D, SolveScalars *sc, int max_cg, double eps) {
+    pdl_enter();
+    constexpr uint32_t kp = 4 * G;
+    __shared__ __align__(16) T qtq[kp * kp];
+    for (uint32_t i = threadIdx.x; i < kp * kp / 4; i += blockDim.x) st4(qtq + i * 4, ldg4(QTQ + i * 4));
+    __syncthreads();
+    double *part_a = sc->partials, *part_b = sc->partials + kPersistMaxBlocks;
+    unsigned *counter = &sc->counter[1];
+    unsigned epoch = 0;
+    const uint32_t lg = threadIdx.x % G;
+    const uint32_t mask = group_mask<G>();
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t nvec = D * (kp / 4);
+    const double g2 = sc->r2[0];
+    double r2 = g2, r2_prev = 0;
+    int it = 0;
+    while (g2 * eps < r2 && it < max_cg) {
+        const T beta = it > 0 ? T(r2 / r2_prev) : T(0);
+        double local = 0;
+        // ---- A: direction, Hv = 0, VQ = V QTQ; whole lane groups stay together (shuffles inside)
+        for (uint64_t f = tid / G; f < ((D + (nthreads / G) - 1) / (nthreads / G)) * (nthreads / G); f += nthreads / G) {
+            const bool ok = f < D;
+            const size_t off = size_t(ok ? f : 0) * kp + lg * 4;
+            V4<T> v = ldcg4(V + off);
+            if (it > 0) {
+                const V4<T> r = ldcg4(R + off);
+                v.x = r.x + beta * v.x; v.y = r.y + beta * v.y; v.z = r.z + beta * v.z; v.w = r.w + beta * v.w;
+            }
+            V4<T> o = zero4<T>();
+#pragma unroll
+            for (int dl = 0; dl < G; ++dl) {
+                const T v0 = __shfl_sync(mask, v.x, dl, G), v1 = __shfl_sync(mask, v.y, dl, G);
+                const T v2 = __shfl_sync(mask, v.z, dl, G), v3 = __shfl_sync(mask, v.w, dl, G);
+                fma4(o, v0, ld4(qtq + (dl * 4 + 0) * kp + lg * 4));
+                fma4(o, v1, ld4(qtq + (dl * 4 + 1) * kp + lg * 4));
+                fma4(o, v2, ld4(qtq + (dl * 4 + 2) * kp + lg * 4));
+                fma4(o, v3, ld4(qtq + (dl * 4 + 3) * kp + lg * 4));
+            }
+            if (ok) {
+                if (it > 0) st4(V + off, v);
+                st4(Hv + off, zero4<T>());
+                st4(VQ + off, o);
+                const T c = freq ? lambda * freq[f] : lambda;
+                local += double(c) * (double(v.x) * v.x + double(v.y) * v.y + double(v.z) * v.z + double(v.w) * v.w);
+            }
+        }
+        grid_barrier(counter, epoch);
+        // ---- B: hs_cross work items
+        for (uint64_t item = tid / G; item < Y.n_items; item += nthreads / G)
+            local += double(hess_cross_item<T, G, true>(Y, X, Q1, ldq, V, VQ, w, Hv, uint32_t(item), 0));
+        local = block_sum(local);
+        if (threadIdx.x == 0) part_a[blockIdx.x] = local;
+        grid_barrier(counter, epoch);
+        // ---- C: step
+        const double vhv = sum_partials(part_a);
+        const T alpha = T(r2 / vhv);
+        local = 0;
+        for (uint64_t i = tid; i < nvec; i += nthreads) {
+            const V4<T> v = ldcg4(V + i * 4);
+            V4<T> h = ldcg4(Hv + i * 4);
+            const T c = freq ? lambda * freq[i / (kp / 4)] : lambda;
+            h.x += c * v.x; h.y += c * v.y; h.z += c * v.z; h.w += c * v.w;
+            V4<T> sv = ldcg4(S + i * 4), r = ldcg4(R + i * 4);
+            sv.x += alpha * v.x; sv.y += alpha * v.y; sv.z += alpha * v.z; sv.w += alpha * v.w;
+            r.x -= alpha * h.x; r.y -= alpha * h.y; r.z -= alpha * h.z; r.w -= alpha * h.w;
+            st4(S + i * 4, sv);
+            st4(R + i * 4, r);
+            local += double(r.x) * r.x + double(r.y) * r.y + double(r.z) * r.z + double(r.w) * r.w;
+        }
+        local = block_sum(local);
+        if (threadIdx.x == 0) part_b[blockIdx.x] = local;
+        grid_barrier(counter, epoch);
+        const double r2n = sum_partials(part_b);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            sc->vHv[it] = vhv;
+            sc->r2[it + 1] = r2n;
+        }
+        r2_prev = r2;
+        r2 = r2n;
+        ++it;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->counter[2] = unsigned(it);
+}
+
 inline unsigned blocks_for(uint64_t groups, int G) {
     const uint64_t threads = groups * uint64_t(G);
     return unsigned((threads + kThreads - 1) / kThreads);
@@ -782,6 +1049,69 @@ void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView
         throw Error(-6, "per-row Gram needs a padded latent dimension of 16 or 32");
 }
 
+
+template <typename T>
+void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, T *R, T *S, T *Hv, const T *freq,
+                     T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
+                     cudaStream_t s) {
+    auto launch = [&](auto kernel) {
+        static int per_sm = 0;
+        if (!per_sm) {
+            OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+            per_sm = std::max(1, std::min(per_sm, kPersistMaxBlocks / kSMs));
+        }
+        int sms = kSMs;
+        int dev = 0;
+        OC_CUDA(cudaGetDevice(&dev));
+        OC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const unsigned grid = unsigned(std::min(kPersistMaxBlocks, per_sm * sms));
+        OmegaView<T> y = Y;
+        CsrView<T> x = X;
+        void *args[] = {&y, &x, &Q1, &V, &R, &S, &Hv, &freq, &lambda, &w, &n1, &D, &sc, &max_cg, &eps};
+        OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
+        count_launch();
+    };
+    if (diag) {
+        OC_DISPATCH_G(kp, launch(k_cg_side_persist<T, G, true>));
+    } else {
+        OC_DISPATCH_G(kp, launch(k_cg_side_persist<T, G, false>));
+    }
+}
+
+
+template <typename T>
+void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
+                      T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
+                      int max_cg, double eps, cudaStream_t s) {
+    auto launch = [&](auto kernel) {
+        static int per_sm = 0;
+        if (!per_sm) {
+            OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+            per_sm = std::max(1, std::min(per_sm, kPersistMaxBlocks / kSMs));
+        }
+        int sms = kSMs, dev = 0;
+        OC_CUDA(cudaGetDevice(&dev));
+        OC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const unsigned grid = unsigned(std::min(kPersistMaxBlocks, per_sm * sms));
+        OmegaView<T> y = Y;
+        CsrView<T> x = X;
+        void *args[] = {&y, &x, &Q1, &ldq, &QTQ, &V, &R, &S, &Hv, &VQ, &freq, &lambda, &w, &D, &sc, &max_cg, &eps};
+        OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
+        count_launch();
+    };
+    switch (kp) {
+        case 4: launch(k_cg_cross_persist<T, 1>); break;
+        case 8: launch(k_cg_cross_persist<T, 2>); break;
+        case 16: launch(k_cg_cross_persist<T, 4>); break;
+        case 32: launch(k_cg_cross_persist<T, 8>); break;
+        case 64:
+            if constexpr (sizeof(T) == 4) { launch(k_cg_cross_persist<T, 16>); break; }
+            [[fallthrough]];
+        default: throw Error(-6, "cg_cross_persist: padded latent dimension too large for shared memory");
+    }
+}
+bool cg_cross_persist_supported(int kp, size_t elem) { return kp <= 32 || (kp == 64 && elem == 4); }
+
 #define OC_INSTANTIATE(T)                                                                          \
     template void spmm_rows<T>(const CsrView<T> &, const T *, T *, uint32_t, int, cudaStream_t);   \
     template void spmm_update<T>(const CsrView<T> &, const T *, T *, T *, uint32_t, const T *, T *, \
@@ -804,6 +1134,12 @@ void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView
     template void ytilde_add_gap<T>(const OmegaView<T> &, const T *, int, cudaStream_t);           \
     template void rowwise_dot<T>(const T *, const T *, uint32_t, int, T *, int, cudaStream_t);     \
     template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);         \
+    template void cg_side_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, T *, T *, T *, T *,      \
+                                     const T *, T, T, T, uint64_t, int, bool, SolveScalars *, int, double,      \
+                                     cudaStream_t);                                                             \
+    template void cg_cross_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, const T *, T *, \
+                                      T *, T *, T *, T *, const T *, T, T, uint64_t, int, SolveScalars *, int,   \
+                                      double, cudaStream_t);                                                     \
     template void row_gram<T>(const uint32_t *, const uint32_t *, const uint32_t *, uint32_t,      \
                               const uint32_t *, const T *, uint32_t, T *, int, cudaStream_t);      \
     template void hess_heavy_rows<T>(const uint32_t *, uint32_t, const CsrView<T> &, const T *,    \

@@ -38,13 +38,14 @@ class Stats(C.Structure):
                 ("ms_side_update", C.c_double), ("ms_cross_grad", C.c_double), ("ms_cross_cg", C.c_double),
                 ("ms_cross_update", C.c_double), ("hv_launches", C.c_uint64), ("hv_algo_bytes", C.c_uint64),
                 ("hv_ms", C.c_double), ("omega_device_bytes", C.c_uint64), ("row_gram_bytes", C.c_uint64),
-                ("row_gram_builds", C.c_uint64)]
+                ("row_gram_builds", C.c_uint64), ("cg_kernel_ms", C.c_double), ("cg_kernel_algo_bytes", C.c_uint64),
+                ("cg_kernel_launches", C.c_uint64), ("cg_kernel_iters", C.c_uint64)]
 
 
 EXPORTS = [
     "ocffm_abi_version", "ocffm_last_error", "ocffm_device_count", "ocffm_create", "ocffm_destroy",
     "ocffm_comm_unique_id", "ocffm_shard_range", "ocffm_comm_init", "ocffm_set_field", "ocffm_set_labels",
-    "ocffm_set_test_labels", "ocffm_set_hyper", "ocffm_init_model", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
+    "ocffm_set_test_labels", "ocffm_set_hyper", "ocffm_init_model", "ocffm_mirror_block", "ocffm_set_block", "ocffm_get_block", "ocffm_init_state",
     "ocffm_solve_block", "ocffm_one_epoch", "ocffm_grad", "ocffm_hess_vec", "ocffm_cg",
     "ocffm_objective", "ocffm_validate", "ocffm_get_vec", "ocffm_get_embed", "ocffm_get_csc",
     "ocffm_get_stats", "ocffm_reset_stats", "ocffm_synchronize", "ocffm_stream",
@@ -79,6 +80,7 @@ def lib():
         L.ocffm_get_block.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
         L.ocffm_init_state.argtypes = [vp]
         L.ocffm_init_model.argtypes = [vp, C.c_uint64]
+        L.ocffm_mirror_block.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, f64p, C.c_uint64]
         L.ocffm_set_hyper.argtypes = [vp, C.c_double, C.c_double, C.c_double]
         L.ocffm_solve_block.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.ocffm_one_epoch.argtypes = [vp]
@@ -241,6 +243,14 @@ class Problem:
                 out[(f1, f2, which)] = rng.uniform(-s, s, size=(self.block_rows(f1, f2, which), self.k))
                 self.set_block(f1, f2, which, out[(f1, f2, which)])
         return out
+
+    def mirror_block(self, f1, f2, which, pinned: Optional[np.ndarray]):
+        """Register (or, with None, drop) a pinned float64 [rows, k] host mirror of a block half:
+        one_epoch() keeps it current, streaming the block out while the rest of the iteration runs."""
+        rows = self.block_rows(f1, f2, which)
+        if pinned is not None:
+            assert pinned.dtype == np.float64 and pinned.size == rows * self.k and pinned.flags["C_CONTIGUOUS"]
+        self._ck(self.L.ocffm_mirror_block(self.h, f1, f2, ord(which), _p(pinned, C.c_double), rows))
 
     def init_model_device(self, seed: int = 1):
         """Counter-based init on the GPU (ocffm_init_model): same distribution as init_mat, no PCIe."""

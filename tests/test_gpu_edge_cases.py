@@ -166,3 +166,36 @@ def test_device_side_model_init(dt):
     o.one_epoch()
     p.one_epoch()
     assert abs(p.objective() - o.func()) <= 10 * tol * abs(o.func())
+
+
+def test_host_mirrors_are_current_after_every_outer_iteration():
+    """ocffm_mirror_block: pinned fp64 mirrors are filled by one_epoch() itself (block by block on a
+    second stream); they must equal what ocffm_get_block returns afterwards, bit for bit, for every
+    iteration, and stay untouched once unregistered; pageable memory is refused."""
+    import torch
+    synth = importlib.import_module("synth")
+    ds = synth.generate("C1", seed=5, scale=0.1, test_rows=30)
+    p = ocffm.Problem(ds, dtype=ocffm.F32, k=16, lam=4.0, omega=2.0 ** -7, r=-1.0)
+    p.init_model(seed=2)
+    p.init_state()
+    mirrors = {}
+    for f1, f2 in p.blocks():
+        for w in "WH":
+            rows = p.block_rows(f1, f2, w)
+            mirrors[(f1, f2, w)] = torch.zeros((rows, 16), dtype=torch.float64, pin_memory=True).numpy()
+            p.mirror_block(f1, f2, w, mirrors[(f1, f2, w)])
+    with pytest.raises(ocffm.OcffmError):
+        p.mirror_block(0, 0, "W", np.zeros((p.block_rows(0, 0, "W"), 16)))      # not pinned
+    for _ in range(2):
+        p.one_epoch()
+        for key, buf in mirrors.items():
+            assert np.array_equal(buf, p.get_block(*key)), key
+    key0 = sorted(mirrors)[0]
+    p.mirror_block(*key0, None)
+    before = mirrors[key0].copy()
+    p.one_epoch()
+    assert np.array_equal(mirrors[key0], before)                     # unregistered: left alone
+    assert not np.array_equal(p.get_block(*key0), before)            # ... although the block moved on
+    for key, buf in mirrors.items():
+        if key != key0:
+            assert np.array_equal(buf, p.get_block(*key)), key
