@@ -434,15 +434,25 @@ struct Problem final : CtxBase {
     DevBuf<T> G, S, R, V, VQ, Hv, Tm, XS, gap, ysum, GT, oQ, bQ, vecKc;
     DevBuf<double> gram64, acc64;
     SolveScalars *sc = nullptr;
-    double *h_scal = nullptr;  // pinned
+    // pinned AND mapped: the CG kernels store g2 / r2 / iteration counts straight into host memory, so the
+    // host never issues a small D2H memcpy inside a solve (it would queue behind the bulk DMA of the host
+    // mirrors on the same copy engine)
+    double *h_scal = nullptr, *d_hscal = nullptr;
+    unsigned *d_hiters = nullptr;
     double *h_stage = nullptr; // pinned staging for model blocks crossing the ABI as fp64
     size_t h_stage_n = 0;
     DevBuf<double> d_stage;
     cudaEvent_t cg_ev[24], g2_ev;
     // host mirrors: blocks are streamed out on a second stream while the rest of the iteration runs
+    // (conversion to fp64 runs on the compute stream -- a tenth of a millisecond per block -- into one of
+    // kMirSlots staging buffers; only the DMA runs on the copy stream, so no second-stream kernel has to
+    // fight the solver's CTAs for SM slots)
+    static constexpr int kMirSlots = 8;
     cudaStream_t copy_st = nullptr;
-    cudaEvent_t solved_ev = nullptr;
-    DevBuf<double> mir_stage;
+    cudaEvent_t mir_ready[kMirSlots] = {}, mir_free[kMirSlots] = {};
+    DevBuf<double> mir_stage[kMirSlots];
+    bool mir_used[kMirSlots] = {};
+    int mir_next = 0;
     uint64_t mirrors = 0, mirrored_bytes = 0;
 
     // stats
@@ -464,7 +474,8 @@ struct Problem final : CtxBase {
         OC_CUDA(cudaGetDevice(&device));
         OC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         OC_CUDA(cudaMalloc(&sc, sizeof(SolveScalars)));
-        OC_CUDA(cudaMallocHost(&h_scal, 64 * sizeof(double)));
+        OC_CUDA(cudaHostAlloc(&h_scal, 64 * sizeof(double), cudaHostAllocMapped));
+        OC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_hscal), h_scal, 0));
         for (auto &e : cg_ev) OC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         OC_CUDA(cudaEventCreateWithFlags(&g2_ev, cudaEventDisableTiming));
         XU.resize(fu);
@@ -520,7 +531,10 @@ struct Problem final : CtxBase {
         if (h_iters) cudaFreeHost(h_iters);
         if (h_stage) cudaFreeHost(h_stage);
         if (copy_st) { cudaStreamSynchronize(copy_st); cudaStreamDestroy(copy_st); }
-        if (solved_ev) cudaEventDestroy(solved_ev);
+        for (int i = 0; i < kMirSlots; ++i) {
+            if (mir_ready[i]) cudaEventDestroy(mir_ready[i]);
+            if (mir_free[i]) cudaEventDestroy(mir_free[i]);
+        }
         if (st) cudaStreamDestroy(st);
     }
 
@@ -918,20 +932,26 @@ struct Problem final : CtxBase {
         slot = data;
         if (data && !copy_st) {
             OC_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-            OC_CUDA(cudaEventCreateWithFlags(&solved_ev, cudaEventDisableTiming));
+            for (int i = 0; i < kMirSlots; ++i) {
+                OC_CUDA(cudaEventCreateWithFlags(&mir_ready[i], cudaEventDisableTiming));
+                OC_CUDA(cudaEventCreateWithFlags(&mir_free[i], cudaEventDisableTiming));
+            }
         }
     }
     void stream_out(Block &bk) {
-        if (!bk.mirW && !bk.mirH) return;
-        OC_CUDA(cudaEventRecord(solved_ev, st));
-        OC_CUDA(cudaStreamWaitEvent(copy_st, solved_ev, 0));
         for (int which : {'W', 'H'}) {
             double *dst = which == 'W' ? bk.mirW : bk.mirH;
             if (!dst) continue;
             const uint64_t rows = block_rows(bk, which);
-            mir_stage.ensure(rows * k);   // grows only on the first iteration (sized by the largest block)
-            unpad_to_f64<T>(block_mat(bk, which).p, kp, mir_stage.p, rows, k, copy_st);
-            OC_CUDA(cudaMemcpyAsync(dst, mir_stage.p, rows * k * sizeof(double), cudaMemcpyDeviceToHost, copy_st));
+            const int slot = mir_next;
+            mir_next = (mir_next + 1) % kMirSlots;
+            if (mir_used[slot]) OC_CUDA(cudaStreamWaitEvent(st, mir_free[slot], 0));   // its previous DMA has drained
+            unpad_to_f64<T>(block_mat(bk, which).p, kp, mir_stage[slot].p, rows, k, st);
+            OC_CUDA(cudaEventRecord(mir_ready[slot], st));
+            OC_CUDA(cudaStreamWaitEvent(copy_st, mir_ready[slot], 0));
+            OC_CUDA(cudaMemcpyAsync(dst, mir_stage[slot].p, rows * k * sizeof(double), cudaMemcpyDeviceToHost, copy_st));
+            OC_CUDA(cudaEventRecord(mir_free[slot], copy_st));
+            mir_used[slot] = true;
             mirrored_bytes += rows * k * sizeof(double);
         }
     }
@@ -1249,7 +1269,7 @@ struct Problem final : CtxBase {
             hi = rows;
         }
     }
-    void account_hess(const Half &h, uint64_t iters) {
+    void account_hess(const Half &h, uint64_t iters, bool separate_pass = true) {
         const size_t s = sizeof(T);
         const uint64_t nnzY = h.nnzYl, nnzX = h.nnzXl;
         if (h.side) {
@@ -1261,8 +1281,10 @@ struct Problem final : CtxBase {
                                    gather_bytes(h.Dl * k * s, nnzX, k * s) + nnzY * 4 +
                                    gather_bytes(h.n1 * k * s, nnzY, k * s) + h.Dl * k * s;
             algo_bytes += iters * bytes;
-            hv_algo_bytes += iters * bytes;
-            hv_launches += iters;
+            if (separate_pass) {   // (the persistent CG kernel has its own counters)
+                hv_algo_bytes += iters * bytes;
+                hv_launches += iters;
+            }
             nnz_trav += iters * (nnzY + nnzX);
         }
         algo_bytes += iters * 7 * h.Dl * k * s;
@@ -1302,9 +1324,12 @@ struct Problem final : CtxBase {
             reg = T(0);
         }
         if (partial && !slotted) comm.allreduce(&sc->vHv[it], 1, st);   // slice partial -> global V.Hv
-        cg_step<T>(S.p + o, R.p + o, V.p + o, Hv.p + o, len, it, sc, fq, reg, kp, slotted, st);
-        if (partial) comm.allreduce(&sc->r2[it + 1], 1, st);
-        OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
+        cg_step<T>(S.p + o, R.p + o, V.p + o, Hv.p + o, len, it, sc, fq, reg, kp, slotted,
+                   partial ? nullptr : d_hscal + 1 + it, st);
+        if (partial) {   // the slice's share is summed over the ranks first: the host copy comes by memcpy
+            comm.allreduce(&sc->r2[it + 1], 1, st);
+            OC_CUDA(cudaMemcpyAsync(h_scal + 1 + it, &sc->r2[it + 1], sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
         OC_CUDA(cudaEventRecord(cg_ev[it], st));
     }
     // ---- persistent CG (cg_side_persist): iteration counts are read back at the next sync ----------
@@ -1323,7 +1348,7 @@ struct Problem final : CtxBase {
         for (const PendingCg &pc : pending) {
             const int it = int(h_iters[pc.slot]);
             const uint64_t before = algo_bytes;
-            account_hess(pc.h, uint64_t(it));
+            account_hess(pc.h, uint64_t(it), false);
             if (pc.ev >= 0) {   // a profiled cross solve: the fused kernel's time and ALL its algorithmic bytes
                 float t = 0;
                 if (cudaEventElapsedTime(&t, cgk_events[pc.ev].first, cgk_events[pc.ev].second) == cudaSuccess) cgk_ms += t;
@@ -1342,11 +1367,17 @@ struct Problem final : CtxBase {
     bool persist_eligible(const Half &h) const {
         if (!persist_on || comm.active() || h.X->n_hot) return false;
         if (h.side) return true;
-        return persist_mode >= 2 && !mrow_ready && cg_cross_persist_supported(int(kp), sizeof(T));
+        return persist_mode >= 2 && cg_cross_persist_supported(int(kp), sizeof(T));
     }
     void run_cg_persist(const Half &h, bool add_reg) {
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
-        cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, st);
+        cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, nullptr, st);
+        if (!h_iters) {
+            OC_CUDA(cudaHostAlloc(&h_iters, kIterSlots * sizeof(unsigned), cudaHostAllocMapped));
+            OC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_hiters), h_iters, 0));
+        }
+        if (int(pending.size()) >= kIterSlots) sync();   // (never inside one outer iteration: 2 x blocks << 1024)
+        const int slot = int(pending.size());
         int ev = -1;
         if (profile && !h.side) {
             if (cgk_events_used == cgk_events.size()) {
@@ -1360,15 +1391,13 @@ struct Problem final : CtxBase {
         }
         if (h.side)
             cg_side_persist<T>(h.Yown->view(), h.X->view(), h.Q1, V.p, R.p, S.p, Hv.p, h.freq, T(prm.lambda),
-                               T(prm.omega), T(h.n1), h.D, int(kp), h.X->diagonal && diag_fast, sc, 20, 9e-2, st);
+                               T(prm.omega), T(h.n1), h.D, int(kp), h.X->diagonal && diag_fast, sc, 20, 9e-2, d_hiters + slot, st);
         else
-            cg_cross_persist<T>(h.Yown->view(), h.X->view(), h.Q1, h.ldq, qtq_of(h), V.p, R.p, S.p, Hv.p, VQ.p, h.freq,
-                                T(prm.lambda), T(prm.omega), h.D, int(kp), sc, 20, 9e-2, st);
+            cg_cross_persist<T>(mrow_ready ? h.Yown->light_view() : h.Yown->view(), h.X->view(), h.Q1, h.ldq, qtq_of(h),
+                                V.p, R.p, S.p, Hv.p, VQ.p, h.freq, T(prm.lambda), T(prm.omega), h.D, int(kp), sc, 20,
+                                9e-2, d_hiters + slot, mrow_ready ? h.Yown->heavy_rows.p : nullptr,
+                                mrow_ready ? h.Yown->n_heavy : 0u, mrow_ready ? mrow.p : nullptr, st);
         if (ev >= 0) OC_CUDA(cudaEventRecord(cgk_events[ev].second, st));
-        if (!h_iters) OC_CUDA(cudaMallocHost(&h_iters, kIterSlots * sizeof(unsigned)));
-        if (int(pending.size()) >= kIterSlots) sync();   // (never inside one outer iteration: 2 x blocks << 1024)
-        const int slot = int(pending.size());
-        OC_CUDA(cudaMemcpyAsync(h_iters + slot, &sc->counter[2], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         pending.push_back(PendingCg{h, slot, ev});
     }
 
@@ -1383,12 +1412,12 @@ struct Problem final : CtxBase {
         if (h.side) mrow_ready = false;
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
         cg_init<T>(G.p + o, h.W1 + o, fq, add_reg ? T(prm.lambda) : T(0), R.p + o, V.p + o, S.p + o, h.s1 - h.s0,
-                   kp, sc, st);
+                   kp, sc, h.sliced ? nullptr : d_hscal, st);
         if (h.sliced) comm.allreduce(&sc->r2[0], 1, st);
         // No hard stream sync in here: g2 is fetched asynchronously while iteration 0 (which the
         // device gate closes by itself when g2 == 0) is already enqueued, and after the loop the
         // stream order alone protects S / R / V -- the GPU never waits for the host.
-        OC_CUDA(cudaMemcpyAsync(h_scal, &sc->r2[0], sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h.sliced) OC_CUDA(cudaMemcpyAsync(h_scal, &sc->r2[0], sizeof(double), cudaMemcpyDeviceToHost, st));
         OC_CUDA(cudaEventRecord(g2_ev, st));
         const int max_cg = 20;
         const double eps = 9e-2;
@@ -1514,7 +1543,7 @@ struct Problem final : CtxBase {
             uint64_t mx = 0;
             for (auto &bk : blocks)
                 if (bk.exists) mx = std::max(mx, std::max(block_rows(bk, 'W'), block_rows(bk, 'H')));
-            mir_stage.ensure(mx * k);
+            for (auto &b : mir_stage) b.ensure(mx * k);
         }
         auto solve = [&](uint32_t f1, uint32_t f2) {
             solve_block(f1, f2);

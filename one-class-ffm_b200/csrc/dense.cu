@@ -256,7 +256,7 @@ k_convert(const double *__restrict__ src, T *__restrict__ dst, uint64_t n) {
 // Deterministic grid-wide fp64 sum: block partials are combined by the last block to finish in
 // a fixed order, so CG scalars (and therefore the stop test ffm.cpp:780) are bit-identical on
 // every rank that holds the same replicated vectors.
-__device__ __forceinline__ void finish_sum(double local, SolveScalars *sc, double *out) {
+__device__ __forceinline__ void finish_sum(double local, SolveScalars *sc, double *out, double *host_out = nullptr) {
     __shared__ bool is_last;
     local = block_sum(local);
     if (threadIdx.x == 0) {
@@ -272,7 +272,12 @@ __device__ __forceinline__ void finish_sum(double local, SolveScalars *sc, doubl
         for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
             sum += reinterpret_cast<volatile double *>(sc->partials)[i];
         sum = block_sum(sum);
-        if (threadIdx.x == 0) *out = sum;
+        if (threadIdx.x == 0) {
+            *out = sum;
+            // mapped pinned host memory: the host reads the scalar after the kernel's event without a
+            // device-to-host memcpy (which would queue behind bulk DMA on the same copy engine)
+            if (host_out) *host_out = sum;
+        }
     }
 }
 
@@ -340,7 +345,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_init(T *__restrict__ G, const T *__restrict__ W, const T *__restrict__ freq, T lambda,
           T *__restrict__ R, T *__restrict__ V, T *__restrict__ S, uint64_t nvec, int kp4,
-          SolveScalars *sc) {
+          SolveScalars *sc, double *host_out) {
     pdl_enter();
     double local = 0;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -356,7 +361,7 @@ k_cg_init(T *__restrict__ G, const T *__restrict__ W, const T *__restrict__ freq
         st4(S + i * 4, zero4<T>());
         local += double(g.x) * g.x + double(g.y) * g.y + double(g.z) * g.z + double(g.w) * g.w;
     }
-    finish_sum(local, sc, &sc->r2[0]);
+    finish_sum(local, sc, &sc->r2[0], host_out);
 }
 
 template <typename T>
@@ -411,7 +416,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T *__restrict__ Hv,
           uint64_t nvec, int it, SolveScalars *sc, const T *__restrict__ freq, T lambda, int kp4,
-          int slotted) {
+          int slotted, double *host_out) {
     pdl_enter();
     if (!gate_open(Gate{sc, it})) return;
     double vhv = sc->vHv[it];
@@ -439,7 +444,7 @@ k_cg_step(T *__restrict__ S, T *__restrict__ R, const T *__restrict__ V, const T
         st4(R + i * 4, r);
         local += double(r.x) * r.x + double(r.y) * r.y + double(r.z) * r.z + double(r.w) * r.w;
     }
-    finish_sum(local, sc, &sc->r2[it + 1]);
+    finish_sum(local, sc, &sc->r2[it + 1], host_out);
 }
 
 template <typename T>
@@ -469,22 +474,52 @@ k_reduce_sum(const T *__restrict__ x, uint64_t n, int square, double *out64) {
     if (threadIdx.x == 0) atomicAdd(out64, local);
 }
 
-// column sums of a [rows x cols] slice (lda leading dimension): thread c%cols owns a column phase
+// column sums of a [rows x cols] slice (lda leading dimension, cols % 4 == 0): a thread owns one
+// 16-byte column chunk and every (kThreads / chunks)-th row of the CTA's slab, four rows in flight per
+// thread (the first version walked one row per CTA step and ran the 4.1 GB pass of the KDD12 shape at
+// 0.9 TB/s); per-CTA partials are combined in shared memory, then one fp64 atomic per column.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_col_sums(const T *__restrict__ A, uint32_t lda, uint32_t cols, uint32_t row0, uint32_t row1,
            double *out64, uint32_t rows_per_cta) {
     pdl_enter();
+    __shared__ double sh[kThreads][4];
     const uint64_t rbeg = uint64_t(row0) + uint64_t(blockIdx.x) * rows_per_cta;
     const uint64_t rend = min(uint64_t(row1), rbeg + rows_per_cta);
-    const uint32_t lanes_per_row = min(cols, uint32_t(kThreads));
-    const uint32_t rows_in_flight = kThreads / lanes_per_row;
-    const uint32_t c0 = threadIdx.x % lanes_per_row, rsub = threadIdx.x / lanes_per_row;
-    if (rsub >= rows_in_flight) return;
-    for (uint32_t c = c0; c < cols; c += lanes_per_row) {
-        double local = 0;
-        for (uint64_t r = rbeg + rsub; r < rend; r += rows_in_flight) local += double(A[r * lda + c]);
-        atomicAdd(out64 + c, local);
+    const uint32_t chunks = cols / 4;                                   // 16-byte chunks per row
+    for (uint32_t c0 = 0; c0 < chunks; c0 += kThreads) {               // (one pass unless cols > 1024)
+        const uint32_t span = min(chunks - c0, uint32_t(kThreads));    // chunks handled in this pass
+        const uint32_t phases = kThreads / span;                       // rows walked side by side
+        const uint32_t ch = threadIdx.x % span, ph = threadIdx.x / span;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (ph < phases) {
+            const T *base = A + size_t(c0 + ch) * 4;
+            uint64_t r = rbeg + ph;
+            for (; r + 3 * uint64_t(phases) < rend; r += 4 * uint64_t(phases)) {
+                const V4<T> v0 = ldg4(base + r * lda), v1 = ldg4(base + (r + phases) * lda);
+                const V4<T> v2 = ldg4(base + (r + 2 * uint64_t(phases)) * lda), v3 = ldg4(base + (r + 3 * uint64_t(phases)) * lda);
+                a0 += double(v0.x) + double(v1.x) + double(v2.x) + double(v3.x);
+                a1 += double(v0.y) + double(v1.y) + double(v2.y) + double(v3.y);
+                a2 += double(v0.z) + double(v1.z) + double(v2.z) + double(v3.z);
+                a3 += double(v0.w) + double(v1.w) + double(v2.w) + double(v3.w);
+            }
+            for (; r < rend; r += phases) {
+                const V4<T> v = ldg4(base + r * lda);
+                a0 += double(v.x); a1 += double(v.y); a2 += double(v.z); a3 += double(v.w);
+            }
+        }
+        sh[threadIdx.x][0] = a0; sh[threadIdx.x][1] = a1; sh[threadIdx.x][2] = a2; sh[threadIdx.x][3] = a3;
+        __syncthreads();
+        if (threadIdx.x < span) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (uint32_t p = 0; p < phases; ++p) {
+                const double *q = sh[p * span + threadIdx.x];
+                s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
+            }
+            double *o = out64 + size_t(c0 + threadIdx.x) * 4;
+            atomicAdd(o + 0, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); atomicAdd(o + 3, s3);
+        }
+        __syncthreads();
     }
 }
 
@@ -683,11 +718,11 @@ void unpad_to_f64(const T *src, uint32_t ld, double *dst, uint64_t rows, uint32_
 
 template <typename T>
 void cg_init(T *G, const T *W, const T *freq, T lambda, T *R, T *V, T *S, uint64_t D, int kp,
-             SolveScalars *sc, cudaStream_t s) {
+             SolveScalars *sc, double *host_g2, cudaStream_t s) {
     const uint64_t nvec = D * kp / 4;
     if (!nvec) return;
     OC_LAUNCH((k_cg_init<T>), ew_blocks(nvec), kThreads, 0, s, G, W, freq, lambda, R, V, S, nvec,
-              kp / 4, sc);
+              kp / 4, sc, host_g2);
 }
 
 template <typename T>
@@ -709,11 +744,11 @@ void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, 
 
 template <typename T>
 void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc, const T *freq,
-             T lambda, int kp, int slotted, cudaStream_t s) {
+             T lambda, int kp, int slotted, double *host_r2, cudaStream_t s) {
     if (!n) return;
     static_assert(kThreads == kDotSlots, "k_cg_step sums one vpart slot per thread");
     OC_LAUNCH((k_cg_step<T>), ew_blocks(n / 4), kThreads, 0, s, S, R, V, Hv, n / 4, it, sc, freq, lambda,
-              kp / 4, slotted);
+              kp / 4, slotted, host_r2);
 }
 
 template <typename T>
@@ -749,7 +784,8 @@ void col_sums(const T *A, uint32_t lda, uint32_t cols, uint32_t row0, uint32_t r
               cudaStream_t s) {
     if (row1 <= row0 || !cols) return;
     const uint64_t rows = row1 - row0;
-    const uint64_t slabs = std::max<uint64_t>(1, std::min<uint64_t>((rows + 255) / 256, 2 * kSMs));
+    if (cols % 4 != 0 || lda % 4 != 0) throw Error(-6, "col_sums: the column count must be a multiple of 4");
+    const uint64_t slabs = std::max<uint64_t>(1, std::min<uint64_t>((rows + 255) / 256, 8 * kSMs));
     const uint32_t per = uint32_t((rows + slabs - 1) / slabs);
     OC_LAUNCH((k_col_sums<T>), unsigned((rows + per - 1) / per), kThreads, 0, s, A, lda, cols, row0,
               row1, out64, per);
@@ -781,7 +817,7 @@ void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStr
     template void init_uniform<T>(T *, uint64_t, uint32_t, uint32_t, uint64_t, uint64_t, double,    \
                                   cudaStream_t);                                                    \
     template void cg_init<T>(T *, const T *, const T *, T, T *, T *, T *, uint64_t, int,            \
-                             SolveScalars *, cudaStream_t);                                         \
+                             SolveScalars *, double *, cudaStream_t);                               \
     template void cg_dir<T>(T *, const T *, T *, uint64_t, int, SolveScalars *, const T *, T, int,  \
                             uint64_t, uint64_t, int, cudaStream_t);                                 \
     template void rowgemm_dir<T>(T *, const T *, T *, const T *, T, uint64_t, uint64_t, const T *,  \
@@ -789,7 +825,7 @@ void omega_objective(const T *yt, uint64_t nnz, T w, T r, double *out64, cudaStr
     template void cg_reg_dot<T>(T *, const T *, const T *, T, uint64_t, int, int, SolveScalars *,   \
                                 int, cudaStream_t);                                                 \
     template void cg_step<T>(T *, T *, const T *, const T *, uint64_t, int, SolveScalars *,         \
-                             const T *, T, int, int, cudaStream_t);                                 \
+                             const T *, T, int, int, double *, cudaStream_t);                       \
     template void axpy<T>(T *, const T *, T, uint64_t, cudaStream_t);                               \
     template void reduce_sum<T>(const T *, uint64_t, int, double *, cudaStream_t);                  \
     template void col_sums<T>(const T *, uint32_t, uint32_t, uint32_t, uint32_t, double *,          \

@@ -116,14 +116,15 @@ void side_diag_iter(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *
 template <typename T>
 void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, T *R, T *S, T *Hv, const T *freq,
                      T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
-                     cudaStream_t s);
+                     unsigned *host_iters, cudaStream_t s);   // host_iters: mapped pinned, receives the iteration count
 
 // ... and of a cross half (QTQ [kp x kp] of this pair; kp <= 32, or 64 in fp32)
 bool cg_cross_persist_supported(int kp, size_t elem);
 template <typename T>
 void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
                       T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
-                      int max_cg, double eps, cudaStream_t s);
+                      int max_cg, double eps, unsigned *host_iters, const uint32_t *heavy_rows, uint32_t n_heavy,
+                      const T *Mrow, cudaStream_t s);   // n_heavy > 0: Y is the light list, heavy rows use Mrow
 
 // y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
 template <typename T>
@@ -195,7 +196,7 @@ void init_uniform(T *dst, uint64_t rows, uint32_t k, uint32_t ld, uint64_t seed,
 // G += lambda * (freq ? freq[row] : 1) * W ; R = -G ; V = R ; S = 0 ; sc->r2[0] += ||G||^2
 template <typename T>
 void cg_init(T *G, const T *W, const T *freq, T lambda, T *R, T *V, T *S, uint64_t D, int kp,
-             SolveScalars *sc, cudaStream_t s);
+             SolveScalars *sc, double *host_g2, cudaStream_t s);   // host_*: optional mapped pinned copy of the scalar
 // it > 0: V = R + (r2[it]/r2[it-1]) V ; always Hv = 0
 // vv != 0: also sc->vHv[it] += lambda sum_f c_f |V_f|^2 over rows [sum_lo, sum_hi) (the regulariser's
 // share of V.Hv when the Hessian pass accumulates the data share itself)
@@ -215,7 +216,7 @@ void cg_reg_dot(T *Hv, const T *V, const T *freq, T lambda, uint64_t D, int kp, 
 // (lambda = 0 when Hv already contains the regulariser)
 template <typename T>
 void cg_step(T *S, T *R, const T *V, const T *Hv, uint64_t n, int it, SolveScalars *sc, const T *freq,
-             T lambda, int kp, int slotted, cudaStream_t s);   // slotted: V.Hv = sum(sc->vpart[it])
+             T lambda, int kp, int slotted, double *host_r2, cudaStream_t s);   // slotted: V.Hv = sum(sc->vpart[it])
 template <typename T>
 void axpy(T *y, const T *x, T alpha, uint64_t n, cudaStream_t s);
 // dst[i] = src[pos[i]]: refreshes one orientation of the y-tilde cache from the other

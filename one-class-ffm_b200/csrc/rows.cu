@@ -604,52 +604,60 @@ k_row_gram(const uint32_t *__restrict__ it_slot, const uint32_t *__restrict__ it
 // The kp x kp matrix is read with fully coalesced 16-byte loads: a group of G = kp/4 lanes takes one
 // matrix row per step, the 32/G groups of the warp take rows g*STEPS + step; after the group
 // reduction lane (g, lg < STEPS) owns component g*STEPS + lg of z.
+// one heavy row (one warp): returns this lane's share of V . (X^T z)
+template <typename T, int KP, bool COH>
+__device__ __forceinline__ T hess_heavy_row(const uint32_t *__restrict__ heavy_rows, const CsrView<T> &X,
+                                            const T *__restrict__ M, const T *V, const T *VQ, T w, T *Hv,
+                                            uint32_t slot, int notau) {
+    constexpr int G = KP / 4, NG = 32 / G, STEPS = KP / NG;
+    static_assert(STEPS <= G, "every component of z needs an owner lane");
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t row = heavy_rows[slot];
+    const uint32_t g = lane / G, lg = lane % G;
+    const bool owner = lg < uint32_t(STEPS);
+    const uint32_t zi = g * STEPS + (owner ? lg : 0u);
+    const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
+    V4<T> phi4 = zero4<T>();
+    T phi_o = T(0), tau_o = T(0);
+    for (uint32_t t = xb; t < xe; ++t) {
+        const size_t off = size_t(X.identity ? row : X.idx[t]) * KP;
+        const T v = X.val[t];
+        fma4(phi4, v, COH ? ldcg4(V + off + lg * 4) : ldg4(V + off + lg * 4));
+        phi_o += v * (COH ? __ldcg(V + off + zi) : __ldg(V + off + zi));
+        if (!notau) tau_o += v * (COH ? __ldcg(VQ + off + zi) : __ldg(VQ + off + zi));
+    }
+    const T *Mi = M + size_t(slot) * KP * KP + size_t(g * STEPS) * KP + lg * 4;
+    T d[STEPS];
+#pragma unroll
+    for (int cstep = 0; cstep < STEPS; ++cstep) d[cstep] = dot4(ldg4(Mi + cstep * KP), phi4);
+    T mine = T(0);
+#pragma unroll
+    for (int cstep = 0; cstep < STEPS; ++cstep) {
+        const T sum = gsum<G>(d[cstep], 0xffffffffu);
+        if (lg == uint32_t(cstep)) mine = sum;
+    }
+    T vhv = T(0);
+    if (owner) {
+        const T z = (T(1) - w) * mine + w * tau_o;
+        vhv = phi_o * z;
+        for (uint32_t t = xb; t < xe; ++t)
+            atomicAdd(scatter_row(X, Hv, X.identity ? row : X.idx[t], KP) + zi, z * X.val[t]);
+    }
+    return vhv;
+}
+
 template <typename T, int KP>
 __global__ void __launch_bounds__(kThreads)
 k_hess_heavy(const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy, CsrView<T> X,
              const T *__restrict__ M, const T *__restrict__ V, const T *__restrict__ VQ, T w,
              T *__restrict__ Hv, Gate gate, double *__restrict__ dot_out, int notau) {
     pdl_enter();
-    constexpr int G = KP / 4, NG = 32 / G, STEPS = KP / NG;
-    static_assert(STEPS <= G, "every component of z needs an owner lane");
     if (!gate_open(gate)) return;
-    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     T vhv = T(0);
-    if (slot < n_heavy) {
-        const uint32_t row = heavy_rows[slot];
-        const uint32_t g = lane / G, lg = lane % G;
-        const bool owner = lg < uint32_t(STEPS);
-        const uint32_t zi = g * STEPS + (owner ? lg : 0u);
-        const uint32_t xb = X.diagonal ? row : X.rowptr[row], xe = X.diagonal ? row + 1 : X.rowptr[row + 1];
-        V4<T> phi4 = zero4<T>();
-        T phi_o = T(0), tau_o = T(0);
-        for (uint32_t t = xb; t < xe; ++t) {
-            const size_t off = size_t(X.identity ? row : X.idx[t]) * KP;
-            const T v = X.val[t];
-            fma4(phi4, v, ldg4(V + off + lg * 4));
-            phi_o += v * __ldg(V + off + zi);
-            if (!notau) tau_o += v * __ldg(VQ + off + zi);
-        }
-        const T *Mi = M + size_t(slot) * KP * KP + size_t(g * STEPS) * KP + lg * 4;
-        T d[STEPS];
-#pragma unroll
-        for (int cstep = 0; cstep < STEPS; ++cstep) d[cstep] = dot4(ldg4(Mi + cstep * KP), phi4);
-        T mine = T(0);
-#pragma unroll
-        for (int cstep = 0; cstep < STEPS; ++cstep) {
-            const T sum = gsum<G>(d[cstep], 0xffffffffu);
-            if (lg == uint32_t(cstep)) mine = sum;
-        }
-        if (owner) {
-            const T z = (T(1) - w) * mine + w * tau_o;
-            vhv = phi_o * z;
-            for (uint32_t t = xb; t < xe; ++t)
-                atomicAdd(scatter_row(X, Hv, X.identity ? row : X.idx[t], KP) + zi, z * X.val[t]);
-        }
-    }
+    if (slot < n_heavy) vhv = hess_heavy_row<T, KP, false>(heavy_rows, X, M, V, VQ, w, Hv, slot, notau);
     if (dot_out) warp_add_slot(double(vhv), dot_out, kDotSlots);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // A whole CG solve of a same-side half (cg, ffm.cpp:744-813 with hs_side, ffm.cpp:594-628) in ONE
@@ -700,7 +708,7 @@ template <typename T, int G, bool DIAG>
 __global__ void __launch_bounds__(kThreads)
 k_cg_side_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__restrict__ V, T *__restrict__ R,
                   T *__restrict__ S, T *__restrict__ Hv, const T *__restrict__ freq, T lambda, T w, T n1,
-                  uint64_t D, SolveScalars *sc, int max_cg, double eps) {
+                  uint64_t D, SolveScalars *sc, int max_cg, double eps, unsigned *host_iters) {
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
     double *part_a = sc->partials, *part_b = sc->partials + kPersistMaxBlocks;
@@ -797,7 +805,10 @@ k_cg_side_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__r
         r2 = r2n;
         ++it;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) sc->counter[2] = unsigned(it);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->counter[2] = unsigned(it);
+        if (host_iters) *host_iters = unsigned(it);   // mapped pinned host memory: no D2H memcpy needed
+    }
 }
 
 
@@ -809,7 +820,10 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, OC_GATHER_MINB)
 k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint32_t ldq, const T *__restrict__ QTQ,
                    T *__restrict__ V, T *__restrict__ R, T *__restrict__ S, T *__restrict__ Hv, T *__restrict__ VQ,
-                   const T *__restrict__ freq, T lambda, T w, uint64_t D, SolveScalars *sc, int max_cg, double eps) {
+                   const T *__restrict__ freq, T lambda, T w, uint64_t D, SolveScalars *sc, int max_cg, double eps,
+                   unsigned *host_iters, const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy,
+                   const T *__restrict__ Mrow) {
+    // heavy_rows / Mrow: the rows served by their per-row observed Gram blocks (Y is then the light list)
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
     __shared__ __align__(16) T qtq[kp * kp];
@@ -859,6 +873,10 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
         // ---- B: hs_cross work items
         for (uint64_t item = tid / G; item < Y.n_items; item += nthreads / G)
             local += double(hess_cross_item<T, G, true>(Y, X, Q1, ldq, V, VQ, w, Hv, uint32_t(item), 0));
+        if constexpr (kp == 16 || kp == 32) {
+            for (uint64_t slot = tid >> 5; slot < n_heavy; slot += nthreads >> 5)
+                local += double(hess_heavy_row<T, int(kp), true>(heavy_rows, X, Mrow, V, VQ, w, Hv, uint32_t(slot), 0));
+        }
         local = block_sum(local);
         if (threadIdx.x == 0) part_a[blockIdx.x] = local;
         grid_barrier(counter, epoch);
@@ -890,7 +908,10 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
         r2 = r2n;
         ++it;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) sc->counter[2] = unsigned(it);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->counter[2] = unsigned(it);
+        if (host_iters) *host_iters = unsigned(it);   // mapped pinned host memory: no D2H memcpy needed
+    }
 }
 
 inline unsigned blocks_for(uint64_t groups, int G) {
@@ -1053,7 +1074,7 @@ void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView
 template <typename T>
 void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, T *R, T *S, T *Hv, const T *freq,
                      T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
-                     cudaStream_t s) {
+                     unsigned *host_iters, cudaStream_t s) {
     auto launch = [&](auto kernel) {
         static int per_sm = 0;
         if (!per_sm) {
@@ -1067,7 +1088,7 @@ void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T 
         const unsigned grid = unsigned(std::min(kPersistMaxBlocks, per_sm * sms));
         OmegaView<T> y = Y;
         CsrView<T> x = X;
-        void *args[] = {&y, &x, &Q1, &V, &R, &S, &Hv, &freq, &lambda, &w, &n1, &D, &sc, &max_cg, &eps};
+        void *args[] = {&y, &x, &Q1, &V, &R, &S, &Hv, &freq, &lambda, &w, &n1, &D, &sc, &max_cg, &eps, &host_iters};
         OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
         count_launch();
     };
@@ -1082,7 +1103,8 @@ void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T 
 template <typename T>
 void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
                       T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
-                      int max_cg, double eps, cudaStream_t s) {
+                      int max_cg, double eps, unsigned *host_iters, const uint32_t *heavy_rows, uint32_t n_heavy,
+                      const T *Mrow, cudaStream_t s) {
     auto launch = [&](auto kernel) {
         static int per_sm = 0;
         if (!per_sm) {
@@ -1095,7 +1117,8 @@ void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, u
         const unsigned grid = unsigned(std::min(kPersistMaxBlocks, per_sm * sms));
         OmegaView<T> y = Y;
         CsrView<T> x = X;
-        void *args[] = {&y, &x, &Q1, &ldq, &QTQ, &V, &R, &S, &Hv, &VQ, &freq, &lambda, &w, &D, &sc, &max_cg, &eps};
+        void *args[] = {&y, &x, &Q1, &ldq, &QTQ, &V, &R, &S, &Hv, &VQ, &freq, &lambda, &w, &D, &sc, &max_cg, &eps, &host_iters,
+                        &heavy_rows, &n_heavy, &Mrow};
         OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
         count_launch();
     };
@@ -1136,10 +1159,10 @@ bool cg_cross_persist_supported(int kp, size_t elem) { return kp <= 32 || (kp ==
     template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);         \
     template void cg_side_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, T *, T *, T *, T *,      \
                                      const T *, T, T, T, uint64_t, int, bool, SolveScalars *, int, double,      \
-                                     cudaStream_t);                                                             \
+                                     unsigned *, cudaStream_t);                                                 \
     template void cg_cross_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, const T *, T *, \
                                       T *, T *, T *, T *, const T *, T, T, uint64_t, int, SolveScalars *, int,   \
-                                      double, cudaStream_t);                                                     \
+                                      double, unsigned *, const uint32_t *, uint32_t, const T *, cudaStream_t);  \
     template void row_gram<T>(const uint32_t *, const uint32_t *, const uint32_t *, uint32_t,      \
                               const uint32_t *, const T *, uint32_t, T *, int, cudaStream_t);      \
     template void hess_heavy_rows<T>(const uint32_t *, uint32_t, const CsrView<T> &, const T *,    \
