@@ -110,6 +110,7 @@ struct Comm {
     ~Comm() {
         close_peers();
         if (area_owned) cudaFree(area_owned);
+        if (karea_owned) cudaFree(karea_owned);
         if (peer_err_host) cudaFreeHost(peer_err_host);
         if (comm) Nccl::get().CommDestroy(comm);
     }
@@ -221,6 +222,28 @@ struct Comm {
         OC_CUDA(cudaMemcpyAsync(&total, agree.p, sizeof(float), cudaMemcpyDeviceToHost, s));
         OC_CUDA(cudaStreamSynchronize(s));
         return total == float(nranks);
+    }
+    // second, tiny area for the scalar reductions INSIDE the persistent CG kernels (kernels.h PeerK)
+    PeerK pk{};
+    bool peerk_ok = false;
+    uint4 *karea_owned = nullptr;
+    void peerk_setup(cudaStream_t s) {
+        pk.nranks = 1;
+        if (!peer_ok) return;
+        if (const char *e = getenv("OCFFM_PEER_KERNEL")) if (atoi(e) == 0) return;
+        const size_t bytes = size_t(2) * nranks * sizeof(uint4);
+        if (cudaMalloc(&karea_owned, bytes + sizeof(unsigned)) != cudaSuccess) { karea_owned = nullptr; cudaGetLastError(); }
+        if (karea_owned) OC_CUDA(cudaMemsetAsync(karea_owned, 0, bytes + sizeof(unsigned), s));
+        void *mapped[kPeerMaxRanks] = {};
+        void *mine = karea_owned;   // share() is collective: a rank whose allocation failed exports a null handle -> all fall back
+        const bool ok = share(mine, mapped, s);
+        if (!ok || !karea_owned) return;
+        for (int q = 0; q < nranks; ++q) pk.area[q] = static_cast<uint4 *>(mapped[q]);
+        pk.nranks = nranks;
+        pk.rank = rank;
+        pk.seq = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(karea_owned) + bytes);
+        pk.error = pv.error;
+        peerk_ok = true;
     }
     unsigned long long gather_seq = 0;
     template <typename T>
@@ -569,6 +592,7 @@ struct Problem final : CtxBase {
             memcpy(&uid, id, sizeof(uid));
             OC_NCCL(Nccl::get().CommInitRank(&comm.comm, nranks, uid, rank));
             comm.peer_setup(st);
+            comm.peerk_setup(st);
         }
     }
     uint32_t lo(uint64_t rows) const { return uint32_t(rows * comm.rank / comm.nranks); }
@@ -1365,13 +1389,22 @@ struct Problem final : CtxBase {
     }
     int persist_mode = 2;              // OCFFM_PERSIST_CG: 0 off, 1 same-side halves only, 2 cross halves too
     bool persist_eligible(const Half &h) const {
-        if (!persist_on || comm.active() || h.X->n_hot) return false;
+        if (!persist_on || h.X->n_hot) return false;
+        // several ranks: only halves whose CG vectors are per-rank slices (identity fields); the two scalars
+        // of an iteration are summed over the ranks inside the kernel (PeerK)
+        if (comm.active() && !(h.sliced && comm.peerk_ok)) return false;
         if (h.side) return true;
         return persist_mode >= 2 && cg_cross_persist_supported(int(kp), sizeof(T));
     }
     void run_cg_persist(const Half &h, bool add_reg) {
+        const size_t o = h.soff() * kp;
+        const uint64_t Ds = h.s1 - h.s0;
         OC_CUDA(cudaMemsetAsync(sc, 0, sizeof(SolveScalars), st));
-        cg_init<T>(G.p, h.W1, h.freq, add_reg ? T(prm.lambda) : T(0), R.p, V.p, S.p, h.D, kp, sc, nullptr, st);
+        cg_init<T>(G.p + o, h.W1 + o, h.freq ? h.freq + h.soff() : nullptr, add_reg ? T(prm.lambda) : T(0), R.p + o,
+                   V.p + o, S.p + o, Ds, kp, sc, nullptr, st);
+        if (h.sliced) comm.allreduce(&sc->r2[0], 1, st);
+        PeerK pk = comm.pk;
+        if (!h.sliced) pk.nranks = 1;
         if (!h_iters) {
             OC_CUDA(cudaHostAlloc(&h_iters, kIterSlots * sizeof(unsigned), cudaHostAllocMapped));
             OC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_hiters), h_iters, 0));
@@ -1391,12 +1424,13 @@ struct Problem final : CtxBase {
         }
         if (h.side)
             cg_side_persist<T>(h.Yown->view(), h.X->view(), h.Q1, V.p, R.p, S.p, Hv.p, h.freq, T(prm.lambda),
-                               T(prm.omega), T(h.n1), h.D, int(kp), h.X->diagonal && diag_fast, sc, 20, 9e-2, d_hiters + slot, st);
+                               T(prm.omega), T(h.n1), Ds, int(kp), h.X->diagonal && (diag_fast || h.sliced), sc, 20, 9e-2,
+                               d_hiters + slot, h.s0, pk, st);
         else
             cg_cross_persist<T>(mrow_ready ? h.Yown->light_view() : h.Yown->view(), h.X->view(), h.Q1, h.ldq, qtq_of(h),
-                                V.p, R.p, S.p, Hv.p, VQ.p, h.freq, T(prm.lambda), T(prm.omega), h.D, int(kp), sc, 20,
+                                V.p, R.p, S.p, Hv.p, VQ.p, h.freq, T(prm.lambda), T(prm.omega), Ds, int(kp), sc, 20,
                                 9e-2, d_hiters + slot, mrow_ready ? h.Yown->heavy_rows.p : nullptr,
-                                mrow_ready ? h.Yown->n_heavy : 0u, mrow_ready ? mrow.p : nullptr, st);
+                                mrow_ready ? h.Yown->n_heavy : 0u, mrow_ready ? mrow.p : nullptr, h.s0, pk, st);
         if (ev >= 0) OC_CUDA(cudaEventRecord(cgk_events[ev].second, st));
         pending.push_back(PendingCg{h, slot, ev});
     }

@@ -42,6 +42,7 @@ struct OmegaView {
     uint64_t nnz_local;
 };
 
+constexpr int kPeerMaxRanksK = 16;
 struct SolveScalars {       // device-resident fp64 scalars of one CG solve (ffm.cpp:761-811)
     double r2[24];          // r2[it] = ||R||^2 before iteration it; r2[0] = g2 = ||G||^2
     double vHv[24];
@@ -111,12 +112,26 @@ template <typename T>
 void side_diag_iter(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, const T *R, T *Hv,
                     const T *freq, T lambda, T w, T n1, int kp, int it, SolveScalars *sc, cudaStream_t s);
 
+// In-kernel scalar all-reduce of the persistent CG kernels on multi-rank contexts: a second, tiny
+// peer-memory area (2 slots x nranks 16-byte lines {lo, seq, hi, seq} per rank, same flag-in-data
+// protocol as peer.cu) with its OWN sequence counter that lives on the device -- every rank runs the
+// same number of reductions per kernel (the stop decisions are bit-identical), so the counters stay
+// in step without the host.  nranks <= 1: unused.
+struct PeerK {
+    uint4 *area[kPeerMaxRanksK];   // every rank's area, mapped here (area[rank] is local)
+    int nranks, rank;
+    unsigned *seq;                 // device-resident call counter (last used sequence number)
+    int *error;                    // mapped host flag: a wait timed out
+};
+
 // The whole CG solve of a same-side half in one cooperative launch (single rank, field without hot
 // features): S, R, V as left by cg_init; on return sc->r2[1..it], sc->vHv[0..it-1] and sc->counter[2] = it.
 template <typename T>
 void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, T *R, T *S, T *Hv, const T *freq,
                      T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
-                     unsigned *host_iters, cudaStream_t s);   // host_iters: mapped pinned, receives the iteration count
+                     unsigned *host_iters, uint64_t f0, const PeerK &pk, cudaStream_t s);
+// host_iters: mapped pinned, receives the iteration count.  f0 / D: this rank's feature slice (sliced
+// halves of multi-rank contexts: vectors are indexed globally, the vector passes run on [f0, f0 + D))
 
 // ... and of a cross half (QTQ [kp x kp] of this pair; kp <= 32, or 64 in fp32)
 bool cg_cross_persist_supported(int kp, size_t elem);
@@ -124,7 +139,8 @@ template <typename T>
 void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
                       T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
                       int max_cg, double eps, unsigned *host_iters, const uint32_t *heavy_rows, uint32_t n_heavy,
-                      const T *Mrow, cudaStream_t s);   // n_heavy > 0: Y is the light list, heavy rows use Mrow
+                      const T *Mrow, uint64_t f0, const PeerK &pk, cudaStream_t s);
+// n_heavy > 0: Y is the light list, heavy rows use Mrow
 
 // y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
 template <typename T>

@@ -704,21 +704,76 @@ __device__ __forceinline__ double sum_partials(const double *part) {
     return v;
 }
 
+// ---- multi-rank: one fp64 scalar summed over the ranks inside the kernel (thread 0 of CTA 0) ----------
+__device__ __forceinline__ double peerk_sum(const PeerK &pk, double v, unsigned seq) {
+    const int slot = int(seq & 1u);
+    const unsigned long long bits = __double_as_longlong(v);
+    const uint32_t lo = uint32_t(bits), hi = uint32_t(bits >> 32);
+    for (int q = 0; q < pk.nranks; ++q)
+        if (q != pk.rank)
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pk.area[q] + slot * pk.nranks + pk.rank),
+                         "r"(lo), "r"(seq), "r"(hi), "r"(seq)
+                         : "memory");
+    double acc = 0;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int q = 0; q < pk.nranks; ++q) {
+        if (q == pk.rank) { acc += v; continue; }
+        const uint4 *src = pk.area[pk.rank] + slot * pk.nranks + q;
+        uint4 x;
+        for (uint32_t spin = 1;; ++spin) {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(src) : "memory");
+            if (x.y == seq && x.w == seq) break;
+            if ((spin & 0x3ffu) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 30ull * 1000 * 1000 * 1000) {   // a peer died: report, end the solve (NaN fails the stop test)
+                    atomicExch(pk.error, 1);
+                    return __longlong_as_double(0x7ff8000000000000ll);
+                }
+            }
+        }
+        acc += __longlong_as_double((unsigned long long)(x.z) << 32 | x.x);
+    }
+    return acc;
+}
+// grid-wide (and, on multi-rank contexts, job-wide) sum of the per-CTA partials; same value in every
+// thread of every CTA of every rank.  One rank: every CTA adds the partials itself.  Several ranks:
+// CTA 0 adds them, exchanges the sum with the peers and publishes the total behind one more barrier.
+__device__ __forceinline__ double global_sum(const double *part, const PeerK &pk, unsigned &kseq, SolveScalars *sc,
+                                             unsigned *counter, unsigned &epoch) {
+    if (pk.nranks <= 1) return sum_partials(part);
+    ++kseq;
+    if (blockIdx.x == 0) {
+        double v = sum_partials(part);
+        if (threadIdx.x == 0) {
+            v = peerk_sum(pk, v, kseq);
+            sc->misc[kseq & 3u] = v;
+        }
+    }
+    grid_barrier(counter, epoch);
+    return __ldcg(&sc->misc[kseq & 3u]);
+}
+
 template <typename T, int G, bool DIAG>
 __global__ void __launch_bounds__(kThreads)
 k_cg_side_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__restrict__ V, T *__restrict__ R,
                   T *__restrict__ S, T *__restrict__ Hv, const T *__restrict__ freq, T lambda, T w, T n1,
-                  uint64_t D, SolveScalars *sc, int max_cg, double eps, unsigned *host_iters) {
+                  uint64_t D, SolveScalars *sc, int max_cg, double eps, unsigned *host_iters, uint64_t f0, PeerK pk) {
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
     double *part_a = sc->partials, *part_b = sc->partials + kPersistMaxBlocks;
     unsigned *counter = &sc->counter[1];
     unsigned epoch = 0;
+    unsigned kseq = pk.nranks > 1 ? *pk.seq : 0u;   // written only at the end of a kernel: every thread reads the same value
     const uint32_t lg = threadIdx.x % G;
     const uint32_t mask = group_mask<G>();
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
     const uint64_t nvec = D * (kp / 4);
     const uint32_t rows = X.row1 - X.row0;
+    // the vector passes run on this rank's slice [f0, f0 + D) (f0 = 0 on one rank); row passes index globally
+    T *Vs = V + f0 * kp, *Rs = R + f0 * kp, *Ss = S + f0 * kp, *Hvs = Hv + f0 * kp;
+    const T *freqs = freq ? freq + f0 : nullptr;
     const double g2 = sc->r2[0];
     double r2 = g2, r2_prev = 0;   // carried in registers: L1 is not coherent with block 0's stores to sc->r2[]
     int it = 0;
@@ -776,27 +831,27 @@ k_cg_side_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__r
         local = block_sum(local);
         if (threadIdx.x == 0) part_a[blockIdx.x] = local;
         grid_barrier(counter, epoch);
-        const double vhv = sum_partials(part_a);
+        const double vhv = global_sum(part_a, pk, kseq, sc, counter, epoch);
         const T alpha = T(r2 / vhv);
         local = 0;
         for (uint64_t i = tid; i < nvec; i += nthreads) {
-            const V4<T> v = ldcg4(V + i * 4);
-            V4<T> h = ldcg4(Hv + i * 4);
+            const V4<T> v = ldcg4(Vs + i * 4);
+            V4<T> h = ldcg4(Hvs + i * 4);
             if (!DIAG) {   // Hv holds the data term only: add lambda c_f V here (ffm.cpp:788-790)
-                const T c = freq ? lambda * freq[i / (kp / 4)] : lambda;
+                const T c = freqs ? lambda * freqs[i / (kp / 4)] : lambda;
                 h.x += c * v.x; h.y += c * v.y; h.z += c * v.z; h.w += c * v.w;
             }
-            V4<T> sv = ldcg4(S + i * 4), r = ldcg4(R + i * 4);
+            V4<T> sv = ldcg4(Ss + i * 4), r = ldcg4(Rs + i * 4);
             sv.x += alpha * v.x; sv.y += alpha * v.y; sv.z += alpha * v.z; sv.w += alpha * v.w;
             r.x -= alpha * h.x; r.y -= alpha * h.y; r.z -= alpha * h.z; r.w -= alpha * h.w;
-            st4(S + i * 4, sv);
-            st4(R + i * 4, r);
+            st4(Ss + i * 4, sv);
+            st4(Rs + i * 4, r);
             local += double(r.x) * r.x + double(r.y) * r.y + double(r.z) * r.z + double(r.w) * r.w;
         }
         local = block_sum(local);
         if (threadIdx.x == 0) part_b[blockIdx.x] = local;
         grid_barrier(counter, epoch);
-        const double r2n = sum_partials(part_b);
+        const double r2n = global_sum(part_b, pk, kseq, sc, counter, epoch);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             sc->vHv[it] = vhv;
             sc->r2[it + 1] = r2n;
@@ -808,6 +863,7 @@ k_cg_side_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, T *__r
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->counter[2] = unsigned(it);
         if (host_iters) *host_iters = unsigned(it);   // mapped pinned host memory: no D2H memcpy needed
+        if (pk.nranks > 1) *pk.seq = kseq;
     }
 }
 
@@ -822,7 +878,7 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
                    T *__restrict__ V, T *__restrict__ R, T *__restrict__ S, T *__restrict__ Hv, T *__restrict__ VQ,
                    const T *__restrict__ freq, T lambda, T w, uint64_t D, SolveScalars *sc, int max_cg, double eps,
                    unsigned *host_iters, const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy,
-                   const T *__restrict__ Mrow) {
+                   const T *__restrict__ Mrow, uint64_t f0, PeerK pk) {
     // heavy_rows / Mrow: the rows served by their per-row observed Gram blocks (Y is then the light list)
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
@@ -832,10 +888,14 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
     double *part_a = sc->partials, *part_b = sc->partials + kPersistMaxBlocks;
     unsigned *counter = &sc->counter[1];
     unsigned epoch = 0;
+    unsigned kseq = pk.nranks > 1 ? *pk.seq : 0u;
     const uint32_t lg = threadIdx.x % G;
     const uint32_t mask = group_mask<G>();
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
     const uint64_t nvec = D * (kp / 4);
+    // this rank's feature slice [f0, f0 + D) for the vector passes (f0 = 0 on one rank)
+    T *Vs = V + f0 * kp, *Rs = R + f0 * kp, *Ss = S + f0 * kp, *Hvs = Hv + f0 * kp;
+    const T *freqs = freq ? freq + f0 : nullptr;
     const double g2 = sc->r2[0];
     double r2 = g2, r2_prev = 0;
     int it = 0;
@@ -843,9 +903,10 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
         const T beta = it > 0 ? T(r2 / r2_prev) : T(0);
         double local = 0;
         // ---- A: direction, Hv = 0, VQ = V QTQ; whole lane groups stay together (shuffles inside)
-        for (uint64_t f = tid / G; f < ((D + (nthreads / G) - 1) / (nthreads / G)) * (nthreads / G); f += nthreads / G) {
-            const bool ok = f < D;
-            const size_t off = size_t(ok ? f : 0) * kp + lg * 4;
+        for (uint64_t fl = tid / G; fl < ((D + (nthreads / G) - 1) / (nthreads / G)) * (nthreads / G); fl += nthreads / G) {
+            const bool ok = fl < D;
+            const uint64_t f = f0 + (ok ? fl : 0);
+            const size_t off = size_t(f) * kp + lg * 4;
             V4<T> v = ldcg4(V + off);
             if (it > 0) {
                 const V4<T> r = ldcg4(R + off);
@@ -881,25 +942,25 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
         if (threadIdx.x == 0) part_a[blockIdx.x] = local;
         grid_barrier(counter, epoch);
         // ---- C: step
-        const double vhv = sum_partials(part_a);
+        const double vhv = global_sum(part_a, pk, kseq, sc, counter, epoch);
         const T alpha = T(r2 / vhv);
         local = 0;
         for (uint64_t i = tid; i < nvec; i += nthreads) {
-            const V4<T> v = ldcg4(V + i * 4);
-            V4<T> h = ldcg4(Hv + i * 4);
-            const T c = freq ? lambda * freq[i / (kp / 4)] : lambda;
+            const V4<T> v = ldcg4(Vs + i * 4);
+            V4<T> h = ldcg4(Hvs + i * 4);
+            const T c = freqs ? lambda * freqs[i / (kp / 4)] : lambda;
             h.x += c * v.x; h.y += c * v.y; h.z += c * v.z; h.w += c * v.w;
-            V4<T> sv = ldcg4(S + i * 4), r = ldcg4(R + i * 4);
+            V4<T> sv = ldcg4(Ss + i * 4), r = ldcg4(Rs + i * 4);
             sv.x += alpha * v.x; sv.y += alpha * v.y; sv.z += alpha * v.z; sv.w += alpha * v.w;
             r.x -= alpha * h.x; r.y -= alpha * h.y; r.z -= alpha * h.z; r.w -= alpha * h.w;
-            st4(S + i * 4, sv);
-            st4(R + i * 4, r);
+            st4(Ss + i * 4, sv);
+            st4(Rs + i * 4, r);
             local += double(r.x) * r.x + double(r.y) * r.y + double(r.z) * r.z + double(r.w) * r.w;
         }
         local = block_sum(local);
         if (threadIdx.x == 0) part_b[blockIdx.x] = local;
         grid_barrier(counter, epoch);
-        const double r2n = sum_partials(part_b);
+        const double r2n = global_sum(part_b, pk, kseq, sc, counter, epoch);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             sc->vHv[it] = vhv;
             sc->r2[it + 1] = r2n;
@@ -911,6 +972,7 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->counter[2] = unsigned(it);
         if (host_iters) *host_iters = unsigned(it);   // mapped pinned host memory: no D2H memcpy needed
+        if (pk.nranks > 1) *pk.seq = kseq;
     }
 }
 
@@ -1074,7 +1136,7 @@ void hess_heavy_rows(const uint32_t *heavy_rows, uint32_t n_heavy, const CsrView
 template <typename T>
 void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T *V, T *R, T *S, T *Hv, const T *freq,
                      T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
-                     unsigned *host_iters, cudaStream_t s) {
+                     unsigned *host_iters, uint64_t f0, const PeerK &pk_, cudaStream_t s) {
     auto launch = [&](auto kernel) {
         static int per_sm = 0;
         if (!per_sm) {
@@ -1088,7 +1150,8 @@ void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T 
         const unsigned grid = unsigned(std::min(kPersistMaxBlocks, per_sm * sms));
         OmegaView<T> y = Y;
         CsrView<T> x = X;
-        void *args[] = {&y, &x, &Q1, &V, &R, &S, &Hv, &freq, &lambda, &w, &n1, &D, &sc, &max_cg, &eps, &host_iters};
+        PeerK pk = pk_;
+        void *args[] = {&y, &x, &Q1, &V, &R, &S, &Hv, &freq, &lambda, &w, &n1, &D, &sc, &max_cg, &eps, &host_iters, &f0, &pk};
         OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
         count_launch();
     };
@@ -1104,7 +1167,7 @@ template <typename T>
 void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
                       T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
                       int max_cg, double eps, unsigned *host_iters, const uint32_t *heavy_rows, uint32_t n_heavy,
-                      const T *Mrow, cudaStream_t s) {
+                      const T *Mrow, uint64_t f0, const PeerK &pk_, cudaStream_t s) {
     auto launch = [&](auto kernel) {
         static int per_sm = 0;
         if (!per_sm) {
@@ -1117,8 +1180,9 @@ void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, u
         const unsigned grid = unsigned(std::min(kPersistMaxBlocks, per_sm * sms));
         OmegaView<T> y = Y;
         CsrView<T> x = X;
+        PeerK pk = pk_;
         void *args[] = {&y, &x, &Q1, &ldq, &QTQ, &V, &R, &S, &Hv, &VQ, &freq, &lambda, &w, &D, &sc, &max_cg, &eps, &host_iters,
-                        &heavy_rows, &n_heavy, &Mrow};
+                        &heavy_rows, &n_heavy, &Mrow, &f0, &pk};
         OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
         count_launch();
     };
@@ -1159,10 +1223,11 @@ bool cg_cross_persist_supported(int kp, size_t elem) { return kp <= 32 || (kp ==
     template void fold_hot<T>(const T *, const uint32_t *, uint32_t, T *, int, cudaStream_t);         \
     template void cg_side_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, T *, T *, T *, T *,      \
                                      const T *, T, T, T, uint64_t, int, bool, SolveScalars *, int, double,      \
-                                     unsigned *, cudaStream_t);                                                 \
+                                     unsigned *, uint64_t, const PeerK &, cudaStream_t);                        \
     template void cg_cross_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, const T *, T *, \
                                       T *, T *, T *, T *, const T *, T, T, uint64_t, int, SolveScalars *, int,   \
-                                      double, unsigned *, const uint32_t *, uint32_t, const T *, cudaStream_t);  \
+                                      double, unsigned *, const uint32_t *, uint32_t, const T *, uint64_t,       \
+                                      const PeerK &, cudaStream_t);                                              \
     template void row_gram<T>(const uint32_t *, const uint32_t *, const uint32_t *, uint32_t,      \
                               const uint32_t *, const T *, uint32_t, T *, int, cudaStream_t);      \
     template void hess_heavy_rows<T>(const uint32_t *, uint32_t, const CsrView<T> &, const T *,    \
