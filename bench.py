@@ -43,7 +43,7 @@ CPU_SAMPLE_SCALE = {"C2": 0.2, "C1": 1.0, "C3": 0.02, "C4": 0.02, "C5": 0.1}    
 # --impl reference: the headline workload runs at FULL size (same config as the GPU arm, fewer timed
 # iterations); the multi-million-row shapes stay on a stated sub-sample
 REF_ARM_SCALE = {"C2": 1.0, "C1": 1.0, "C3": 0.02, "C4": 0.02, "C5": 0.1}
-REF_ARM_MAX_STEPS = 3
+REF_ARM_MAX_STEPS = 2
 # BASELINE configs[2..4] shard ONE fixed set over the GPUs (strong scaling); the headline C2 run keeps
 # round 1's weak scaling (one block of 30 000 users per GPU over the same items)
 DEFAULT_SCALING = {"C2": "weak", "C1": "strong", "C3": "strong", "C4": "strong", "C5": "strong"}
