@@ -364,19 +364,24 @@ def main():
                     whole_epoch_gbs_all_gpus=(algo_total / 1e9) / sec,
                     row_gram_builds=int(st.row_gram_builds), row_gram_bytes=int(st.row_gram_bytes))
     if st.cg_kernel_launches:
-        # cross halves solved by the persistent CG kernel: the Hessian row pass is a phase of that kernel,
-        # so the roofline is the fused kernel's -- ALL its algorithmic bytes (per iteration: the hs_cross
-        # formula of SURVEY 8(a) A7 + 7 D k s of CG vector traffic, A8) over its event-timed duration
+        # Cross halves solved by the persistent CG kernel: the hs_cross row pass is a PHASE of that kernel.
+        # Its time is stamped inside the kernel (%globaltimer of CTA 0 between the grid-wide barriers that
+        # bracket the phase, OCFFM_PROFILE=1) and added to the event-timed separate launches above, so
+        # `achieved` / `frac` keep round 1's definition (hs_cross algorithmic bytes over the pass time).
+        # `cg_kernel` is the fused kernel as a whole: ALL its algorithmic bytes (per iteration the hs_cross
+        # formula + 7 D k s of CG vector traffic, SURVEY 8(a) A7 + A8) over its event-timed duration.
         ck_gbs = (st.cg_kernel_algo_bytes / 1e9) / (st.cg_kernel_ms / 1e3)
         roofline.update(
-            kernel="k_cg_cross_persist (one cooperative launch per cross half solve; per CG iteration: direction + V*QTQ, "
-                   "hs_cross row pass (gathers), step; grid-wide barriers in between)",
-            achieved=ck_gbs, frac=ck_gbs / pk["hbm_gbs"], launches=int(st.cg_kernel_launches),
-            avg_launch_ms=st.cg_kernel_ms / st.cg_kernel_launches,
-            avg_cg_iteration_ms=st.cg_kernel_ms / max(1, st.cg_kernel_iters), cg_iterations=int(st.cg_kernel_iters),
-            share_of_step=st.cg_kernel_ms / ms if ms > 0 else None,
-            algo_bytes_per_launch=st.cg_kernel_algo_bytes / st.cg_kernel_launches,
-            separate_hessian_passes=dict(launches=int(st.hv_launches), ms=st.hv_ms, gbs=hv_gbs))
+            kernel="hs_cross row pass: phase of k_cg_cross_persist (one cooperative launch per cross half solve) "
+                   "+ k_hess_cross / k_hess_heavy launches of the halves on the per-iteration kernels",
+            timing="%globaltimer stamps between the grid barriers for the phases, CUDA events for the launches",
+            cg_kernel=dict(kernel="k_cg_cross_persist (per CG iteration: direction + V*QTQ, hs_cross row pass, step)",
+                           achieved=ck_gbs, frac=ck_gbs / pk["hbm_gbs"], launches=int(st.cg_kernel_launches),
+                           avg_launch_ms=st.cg_kernel_ms / st.cg_kernel_launches,
+                           avg_cg_iteration_ms=st.cg_kernel_ms / max(1, st.cg_kernel_iters),
+                           cg_iterations=int(st.cg_kernel_iters),
+                           share_of_step=st.cg_kernel_ms / ms if ms > 0 else None,
+                           algo_bytes_per_launch=st.cg_kernel_algo_bytes / st.cg_kernel_launches))
     free_b, total_b = torch.cuda.mem_get_info(local_rank)
     footprint = dict(omega_device_bytes=int(st.omega_device_bytes), hbm_used_bytes=int(total_b - free_b),
                      note="per rank (rank 0): Omega slices = row pointers, column ids, y-tilde and work-item lists of both orientations")

@@ -462,6 +462,7 @@ struct Problem final : CtxBase {
     // mirrors on the same copy engine)
     double *h_scal = nullptr, *d_hscal = nullptr;
     unsigned *d_hiters = nullptr;
+    float *h_phase = nullptr, *d_hphase = nullptr;   // mapped pinned: row-phase time of every persistent cross launch
     double *h_stage = nullptr; // pinned staging for model blocks crossing the ABI as fp64
     size_t h_stage_n = 0;
     DevBuf<double> d_stage;
@@ -552,6 +553,7 @@ struct Problem final : CtxBase {
         if (sc) cudaFree(sc);
         if (h_scal) cudaFreeHost(h_scal);
         if (h_iters) cudaFreeHost(h_iters);
+        if (h_phase) cudaFreeHost(h_phase);
         if (h_stage) cudaFreeHost(h_stage);
         if (copy_st) { cudaStreamSynchronize(copy_st); cudaStreamDestroy(copy_st); }
         for (int i = 0; i < kMirSlots; ++i) {
@@ -1372,7 +1374,11 @@ struct Problem final : CtxBase {
         for (const PendingCg &pc : pending) {
             const int it = int(h_iters[pc.slot]);
             const uint64_t before = algo_bytes;
-            account_hess(pc.h, uint64_t(it), false);
+            // profiled cross solves: the row phases of the persistent kernel count as Hessian passes (their
+            // time comes from the kernel's own %globaltimer stamps between the grid barriers)
+            const bool timed_rows = pc.ev >= 0;
+            account_hess(pc.h, uint64_t(it), timed_rows);
+            if (timed_rows) hv_ms += double(h_phase[pc.slot]);
             if (pc.ev >= 0) {   // a profiled cross solve: the fused kernel's time and ALL its algorithmic bytes
                 float t = 0;
                 if (cudaEventElapsedTime(&t, cgk_events[pc.ev].first, cgk_events[pc.ev].second) == cudaSuccess) cgk_ms += t;
@@ -1408,6 +1414,8 @@ struct Problem final : CtxBase {
         if (!h_iters) {
             OC_CUDA(cudaHostAlloc(&h_iters, kIterSlots * sizeof(unsigned), cudaHostAllocMapped));
             OC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_hiters), h_iters, 0));
+            OC_CUDA(cudaHostAlloc(&h_phase, kIterSlots * sizeof(float), cudaHostAllocMapped));
+            OC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_hphase), h_phase, 0));
         }
         if (int(pending.size()) >= kIterSlots) sync();   // (never inside one outer iteration: 2 x blocks << 1024)
         const int slot = int(pending.size());
@@ -1430,7 +1438,8 @@ struct Problem final : CtxBase {
             cg_cross_persist<T>(mrow_ready ? h.Yown->light_view() : h.Yown->view(), h.X->view(), h.Q1, h.ldq, qtq_of(h),
                                 V.p, R.p, S.p, Hv.p, VQ.p, h.freq, T(prm.lambda), T(prm.omega), Ds, int(kp), sc, 20,
                                 9e-2, d_hiters + slot, mrow_ready ? h.Yown->heavy_rows.p : nullptr,
-                                mrow_ready ? h.Yown->n_heavy : 0u, mrow_ready ? mrow.p : nullptr, h.s0, pk, st);
+                                mrow_ready ? h.Yown->n_heavy : 0u, mrow_ready ? mrow.p : nullptr, h.s0, pk,
+                                profile ? d_hphase + slot : nullptr, st);
         if (ev >= 0) OC_CUDA(cudaEventRecord(cgk_events[ev].second, st));
         pending.push_back(PendingCg{h, slot, ev});
     }

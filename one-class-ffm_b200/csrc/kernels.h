@@ -139,8 +139,9 @@ template <typename T>
 void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
                       T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
                       int max_cg, double eps, unsigned *host_iters, const uint32_t *heavy_rows, uint32_t n_heavy,
-                      const T *Mrow, uint64_t f0, const PeerK &pk, cudaStream_t s);
-// n_heavy > 0: Y is the light list, heavy rows use Mrow
+                      const T *Mrow, uint64_t f0, const PeerK &pk, float *host_phase_ms, cudaStream_t s);
+// n_heavy > 0: Y is the light list, heavy rows use Mrow.  host_phase_ms (mapped pinned, optional): receives the
+// time this launch spent in its hs_cross row phases (%globaltimer between the grid barriers, CTA 0)
 
 // y-tilde[t] += U_row . Vo[idx[t]]   (update_cross, ffm.cpp:451-464; also init_y_tilde per pair)
 template <typename T>

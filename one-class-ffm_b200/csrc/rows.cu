@@ -7,6 +7,8 @@
 // and a warp works on 32/G rows at once.  Dots over k are group shuffles; X^T(.) scatters are
 // 16-byte REDs (red.global.add.v4.f32 on sm_100a) so no thread-private D x k scratch exists
 // (the reference's G_/Hv_ buffers, ffm.cpp:555-557, 672-674, 759).
+#include <map>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -878,7 +880,7 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
                    T *__restrict__ V, T *__restrict__ R, T *__restrict__ S, T *__restrict__ Hv, T *__restrict__ VQ,
                    const T *__restrict__ freq, T lambda, T w, uint64_t D, SolveScalars *sc, int max_cg, double eps,
                    unsigned *host_iters, const uint32_t *__restrict__ heavy_rows, uint32_t n_heavy,
-                   const T *__restrict__ Mrow, uint64_t f0, PeerK pk) {
+                   const T *__restrict__ Mrow, uint64_t f0, PeerK pk, float *host_phase_ms) {
     // heavy_rows / Mrow: the rows served by their per-row observed Gram blocks (Y is then the light list)
     pdl_enter();
     constexpr uint32_t kp = 4 * G;
@@ -889,6 +891,7 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
     unsigned *counter = &sc->counter[1];
     unsigned epoch = 0;
     unsigned kseq = pk.nranks > 1 ? *pk.seq : 0u;
+    unsigned long long t_b0 = 0, t_rows = 0;   // OCFFM_PROFILE: time of the hs_cross row phases (CTA 0, thread 0)
     const uint32_t lg = threadIdx.x % G;
     const uint32_t mask = group_mask<G>();
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
@@ -931,6 +934,7 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
             }
         }
         grid_barrier(counter, epoch);
+        if (host_phase_ms && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b0));
         // ---- B: hs_cross work items
         for (uint64_t item = tid / G; item < Y.n_items; item += nthreads / G)
             local += double(hess_cross_item<T, G, true>(Y, X, Q1, ldq, V, VQ, w, Hv, uint32_t(item), 0));
@@ -941,6 +945,11 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
         local = block_sum(local);
         if (threadIdx.x == 0) part_a[blockIdx.x] = local;
         grid_barrier(counter, epoch);
+        if (host_phase_ms && blockIdx.x == 0 && threadIdx.x == 0) {   // every CTA has finished the row pass
+            unsigned long long t_b1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b1));
+            t_rows += t_b1 - t_b0;
+        }
         // ---- C: step
         const double vhv = global_sum(part_a, pk, kseq, sc, counter, epoch);
         const T alpha = T(r2 / vhv);
@@ -973,7 +982,20 @@ k_cg_cross_persist(OmegaView<T> Y, CsrView<T> X, const T *__restrict__ Q1, uint3
         sc->counter[2] = unsigned(it);
         if (host_iters) *host_iters = unsigned(it);   // mapped pinned host memory: no D2H memcpy needed
         if (pk.nranks > 1) *pk.seq = kseq;
+        if (host_phase_ms) *host_phase_ms = float(double(t_rows) * 1e-6);
     }
+}
+
+inline int persist_ctas_per_sm(const void *kernel) {
+    static std::map<const void *, int> cache;
+    auto it = cache.find(kernel);
+    if (it != cache.end()) return it->second;
+    int per_sm = 0;
+    OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    OC_REQUIRE(per_sm >= 1, "persistent CG kernel does not fit an SM");
+    per_sm = std::min(per_sm, kPersistMaxBlocks / kSMs);
+    cache[kernel] = per_sm;
+    return per_sm;
 }
 
 inline unsigned blocks_for(uint64_t groups, int G) {
@@ -1138,11 +1160,9 @@ void cg_side_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, T 
                      T lambda, T w, T n1, uint64_t D, int kp, bool diag, SolveScalars *sc, int max_cg, double eps,
                      unsigned *host_iters, uint64_t f0, const PeerK &pk_, cudaStream_t s) {
     auto launch = [&](auto kernel) {
-        static int per_sm = 0;
-        if (!per_sm) {
-            OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-            per_sm = std::max(1, std::min(per_sm, kPersistMaxBlocks / kSMs));
-        }
+        // per kernel INSTANCE (the instantiations for different lane-group sizes share one pointer type, so a
+        // function-local static would be shared between them): co-resident CTAs per SM of this very kernel
+        int per_sm = persist_ctas_per_sm(reinterpret_cast<const void *>(kernel));
         int sms = kSMs;
         int dev = 0;
         OC_CUDA(cudaGetDevice(&dev));
@@ -1167,13 +1187,11 @@ template <typename T>
 void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, uint32_t ldq, const T *QTQ, T *V, T *R,
                       T *S, T *Hv, T *VQ, const T *freq, T lambda, T w, uint64_t D, int kp, SolveScalars *sc,
                       int max_cg, double eps, unsigned *host_iters, const uint32_t *heavy_rows, uint32_t n_heavy,
-                      const T *Mrow, uint64_t f0, const PeerK &pk_, cudaStream_t s) {
+                      const T *Mrow, uint64_t f0, const PeerK &pk_, float *host_phase_ms, cudaStream_t s) {
     auto launch = [&](auto kernel) {
-        static int per_sm = 0;
-        if (!per_sm) {
-            OC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-            per_sm = std::max(1, std::min(per_sm, kPersistMaxBlocks / kSMs));
-        }
+        // per kernel INSTANCE (the instantiations for different lane-group sizes share one pointer type, so a
+        // function-local static would be shared between them): co-resident CTAs per SM of this very kernel
+        int per_sm = persist_ctas_per_sm(reinterpret_cast<const void *>(kernel));
         int sms = kSMs, dev = 0;
         OC_CUDA(cudaGetDevice(&dev));
         OC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1182,7 +1200,7 @@ void cg_cross_persist(const OmegaView<T> &Y, const CsrView<T> &X, const T *Q1, u
         CsrView<T> x = X;
         PeerK pk = pk_;
         void *args[] = {&y, &x, &Q1, &ldq, &QTQ, &V, &R, &S, &Hv, &VQ, &freq, &lambda, &w, &D, &sc, &max_cg, &eps, &host_iters,
-                        &heavy_rows, &n_heavy, &Mrow, &f0, &pk};
+                        &heavy_rows, &n_heavy, &Mrow, &f0, &pk, &host_phase_ms};
         OC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kThreads), args, 0, s));
         count_launch();
     };
@@ -1227,7 +1245,7 @@ bool cg_cross_persist_supported(int kp, size_t elem) { return kp <= 32 || (kp ==
     template void cg_cross_persist<T>(const OmegaView<T> &, const CsrView<T> &, const T *, uint32_t, const T *, T *, \
                                       T *, T *, T *, T *, const T *, T, T, uint64_t, int, SolveScalars *, int,   \
                                       double, unsigned *, const uint32_t *, uint32_t, const T *, uint64_t,       \
-                                      const PeerK &, cudaStream_t);                                              \
+                                      const PeerK &, float *, cudaStream_t);                                     \
     template void row_gram<T>(const uint32_t *, const uint32_t *, const uint32_t *, uint32_t,      \
                               const uint32_t *, const T *, uint32_t, T *, int, cudaStream_t);      \
     template void hess_heavy_rows<T>(const uint32_t *, uint32_t, const CsrView<T> &, const T *,    \

@@ -19,7 +19,10 @@ for w in ("C2", "C4", "C3", "C5"):
         r, ev = d["roofline"], d.get("eval") or {}
         er = ev.get("roofline") or {}
         sep = r.get("separate_hessian_passes") or {}
-        hv_frac = (sep.get("gbs") or 0) / r["peak"] if sep.get("gbs") else (r["frac"] if not r.get("cg_iterations") else None)
+        if "cg_kernel" in r or not r.get("cg_iterations"):
+            hv_frac = r["frac"]                       # all Hessian passes (phases of the persistent kernel + launches)
+        else:                                         # lines written before the phase stamps existed
+            hv_frac = (sep.get("gbs") or 0) / r["peak"] if sep.get("gbs") else None
         rows.append((n, d["config"].get("m"), d["ms_per_step"], d["value"], d["cg_iters_per_step"], r["whole_epoch_frac_per_gpu"],
                      hv_frac, ev.get("ms"), ev.get("users_per_s"), er.get("frac"), er.get("useful_frac"),
                      (d["e2e"] or {}).get("sec_per_step"), d["footprint"]["omega_device_bytes"] / 1e6,
@@ -27,7 +30,7 @@ for w in ("C2", "C4", "C3", "C5"):
     if not rows:
         continue
     out.append(f"**{names[w]}**\n")
-    out.append("| GPUs | users | ms / outer iteration | nnz/s | speed-up | CG it. | whole-iteration HBM frac / GPU | Hessian pass HBM frac / GPU | validate ms | users/s | scorer tensor frac / GPU (3 MMAs per MAC; useful) | e2e ms / step | Ω MB / rank | N-rank == 1-rank |")
+    out.append("| GPUs | users | ms / outer iteration | nnz/s | speed-up | CG it. | whole-iteration HBM frac / GPU | hs_cross row pass, HBM frac / GPU | validate ms | users/s | scorer tensor frac / GPU (3 MMAs per MAC; useful) | e2e ms / step | Ω MB / rank | N-rank == 1-rank |")
     out.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     base = rows[0]
     for (n, m, ms, v, cg, wf, hf, ems, ups, ef, uf, e2e, om, ok) in rows:
