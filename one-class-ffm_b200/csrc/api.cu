@@ -356,8 +356,9 @@ struct Problem final : CtxBase {
     bool fused_dot = true;
     uint32_t hot_min = 16384;   // OCFFM_HOT_MIN: occurrences that make a feature "hot" (0 = off)
     // Per-row observed Gram for the Hessian passes of cross halves (rows.cu "Mrow").  Default: fp32
-    // contexts with kp 16 / 32 (at kp 64 building the Gram costs as much as the gathers it saves;
-    // fp64 contexts are the strict-parity mode and keep the reference's summation structure).
+    // contexts with kp = 32 (at kp 64 building the Gram costs as much as the gathers it saves, at kp 16
+    // it lost 10 ms per outer iteration on the Outbrain shape; fp64 contexts are the strict-parity mode
+    // and keep the reference's summation structure).
     // Building the blocks costs k*k FMAs per pair (16 gather passes' worth of FLOPs at k = 32), so it
     // pays only for half solves with many CG iterations: by default (OCFFM_MROW=1, fp32) a half builds
     // them when its previous solve took >= OCFFM_MROW_ITERS (8) iterations.  OCFFM_MROW=0 never,
@@ -526,7 +527,8 @@ struct Problem final : CtxBase {
         if (const char *e = getenv("OCFFM_MROW_MIN")) mrow_min = uint32_t(std::max(1, atoi(e)));
         if (const char *e = getenv("OCFFM_MROW_ITERS")) mrow_iters = std::max(0, atoi(e));
         if (const char *e = getenv("OCFFM_MROW_CAP_MB")) mrow_cap_bytes = size_t(std::max(1, atoi(e))) << 20;
-        mrow_on = mrow_mode != 0 && row_gram_supported(int(kp)) && (std::is_same<T, float>::value || mrow_mode >= 2);
+        mrow_on = mrow_mode != 0 && row_gram_supported(int(kp)) &&
+                  ((std::is_same<T, float>::value && kp == 32) || mrow_mode >= 2);
         if (const char *e = getenv("OCFFM_DIAG_FAST")) diag_fast = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_NOTAU")) notau_allowed = atoi(e) != 0;
         if (const char *e = getenv("OCFFM_PERSIST_CG")) { persist_mode = atoi(e); persist_on = persist_mode != 0; }
@@ -1393,14 +1395,17 @@ struct Problem final : CtxBase {
         pending.clear();
         cgk_events_used = 0;
     }
-    int persist_mode = 2;              // OCFFM_PERSIST_CG: 0 off, 1 same-side halves only, 2 cross halves too
+    // OCFFM_PERSIST_CG: 0 off, 1 same-side halves only, 2 (default) cross halves too when kp >= 32, 3 cross
+    // halves at every supported kp.  Measured on the Outbrain shape (k = 16, 4-lane groups): the persistent
+    // cross kernel costs 3 ms and the per-row Gram 10 ms per outer iteration there, so both wait for kp >= 32.
+    int persist_mode = 2;
     bool persist_eligible(const Half &h) const {
         if (!persist_on || h.X->n_hot) return false;
         // several ranks: only halves whose CG vectors are per-rank slices (identity fields); the two scalars
         // of an iteration are summed over the ranks inside the kernel (PeerK)
         if (comm.active() && !(h.sliced && comm.peerk_ok)) return false;
         if (h.side) return true;
-        return persist_mode >= 2 && cg_cross_persist_supported(int(kp), sizeof(T));
+        return persist_mode >= 2 && (kp >= 32 || persist_mode >= 3) && cg_cross_persist_supported(int(kp), sizeof(T));
     }
     void run_cg_persist(const Half &h, bool add_reg) {
         const size_t o = h.soff() * kp;

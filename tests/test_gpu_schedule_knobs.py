@@ -54,7 +54,8 @@ def test_schedule_knobs_do_not_change_results(self_side):
     assert abs(base["obj"] - o.func()) <= 1e-9 * abs(o.func())
     # both orientations of the cache hold the same numbers entry for entry
     for env in ({"OCFFM_MIRROR_YT": "0"}, {"OCFFM_FUSED_DOT": "0"}, {"OCFFM_DIAG_FAST": "0"}, {"OCFFM_NOTAU": "1"},
-                {"OCFFM_PERSIST_CG": "0"}, {"OCFFM_PERSIST_CG": "1"}, {"OCFFM_PERSIST_CG": "0", "OCFFM_DIAG_FAST": "0"},
+                {"OCFFM_PERSIST_CG": "0"}, {"OCFFM_PERSIST_CG": "1"}, {"OCFFM_PERSIST_CG": "3"},
+                {"OCFFM_PERSIST_CG": "0", "OCFFM_DIAG_FAST": "0"},
                 {"OCFFM_MIRROR_YT": "0", "OCFFM_FUSED_DOT": "0", "OCFFM_DIAG_FAST": "0", "OCFFM_NOTAU": "1"}):
         _, alt = run(ds, prm, env)
         assert alt["cg"] == base["cg"], env

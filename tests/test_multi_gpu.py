@@ -32,8 +32,10 @@ def test_two_ranks_match_one(dtype, peer):
     if peer == "0" and dtype == "f32":
         pytest.skip("covered by the fp64 case")
     with tempfile.TemporaryDirectory() as tmp:
-        one = run(1, os.path.join(tmp, "one.npz"), dtype)
-        two = run(2, os.path.join(tmp, "two.npz"), dtype, {"OCFFM_PEER": peer})
+        # OCFFM_PERSIST_CG=3: the persistent CG kernels also for cross halves at this small k, so that the
+        # 2-rank run covers their in-kernel scalar all-reduce (peer = 1) as well as the per-iteration path (peer = 0)
+        one = run(1, os.path.join(tmp, "one.npz"), dtype, {"OCFFM_PERSIST_CG": "3"})
+        two = run(2, os.path.join(tmp, "two.npz"), dtype, {"OCFFM_PEER": peer, "OCFFM_PERSIST_CG": "3"})
     tol = 1e-9 if dtype == "f64" else 2e-3
     if dtype == "f64":
         assert list(one["cgs"]) == list(two["cgs"])
