@@ -3,17 +3,25 @@
 on the KKBox-shaped synthetic set (BASELINE.json configs[1], SURVEY.md 8 shape C2), plus
 full-ranking eval users/s, measured through the C ABI of libocffm_cuda.so.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C1..C5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A step is one outer iteration (one_epoch, ffm.cpp:852-870: every side + cross block solve and
 cache_sasb) over the whole synthetic set.  `value` = nnz/s = N_trav / time with N_trav as defined
-in SURVEY.md 8(d) (it normalises out CG-count differences), inputs resident in HBM; `e2e` = the
-same metric when every step starts from a HOST-resident model (H2D of all W/H, state rebuild,
-the epoch, D2H of all W/H).  `--impl reference` times the UNMODIFIED reference's own
-one_epoch()/validate() (oracle/_ref/ref_harness_blas, built from /root/reference by
-oracle/Makefile) on the box's host cores on a bounded sample of the same workload.
-Rank 0 prints ONE JSON line.
+in SURVEY.md 8(d) (it normalises out CG-count differences), inputs resident in HBM; the library's
+counters are per rank and summed over the ranks.  `e2e` = the same metric when every step starts
+from a HOST-resident fp64 model and ends with the host copy current again: H2D of all W/H from
+pinned memory (ocffm_set_block), ocffm_init_state, ocffm_one_epoch with every block registered as
+a host mirror (ocffm_mirror_block: D2H of each block on a second stream right after its solve).
+`roofline`: the hs_cross row pass (algorithmic bytes over the pass time; a phase of the persistent
+CG kernel, stamped inside the kernel), `roofline.cg_kernel`: the fused kernel as a whole; all
+fractions are per GPU.  N > 1: C2 scales WEAK (one block of 30 000 users per GPU), the other
+workloads STRONG (the fixed shape sharded by rows), and every run first checks an N-rank fp64
+solve of a small set against a 1-rank solve (`multi_rank_parity`).
+`--impl reference` times the UNMODIFIED reference's own one_epoch()/validate()
+(oracle/_ref/ref_harness_blas, built from /root/reference by oracle/Makefile) on the box's host
+cores: the FULL C2 shape (1 warm-up + at most 2 timed outer iterations), stated sub-samples for
+the multi-million-row shapes.  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
