@@ -203,6 +203,8 @@ def run_reference_arm(args, shape, k, test_rows):
     sample = (f"{shape} scaled x{scale} (m={ds.m}, n={ds.n}, nnz_y={nnz_y}), k={k}, {len(ep)} timed epochs "
               f"after {args.warmup} warm-up, {threads} OpenMP threads, OpenBLAS pinned to 1 thread")
     return dict(kind=kind, value=value, sec_per_epoch=sec / len(ep), cores=threads, host_cores=ncpu,
+                shape_keys=dict(m=ds.m, n=ds.n, nnz_y=nnz_y, fu=fu, fv=fv, scale=scale,
+                                eval_rows_timed=0 if ds.test is None else ds.test.rows),
                 sample=sample, cg_iters=[e["cg_iters"] for e in ep], wall_s=wall,
                 eval_users_per_s=(res["m_t"] / res["validate_s"]) if "validate_s" in res else None,
                 harness=os.path.basename(harness))
@@ -250,7 +252,7 @@ def main():
         if ref is None:
             print(json.dumps(dict(impl="reference", unavailable="oracle/_ref binaries missing (make -C oracle ref)")))
             return
-        config.update(sample=ref["sample"])
+        config.update(sample=ref["sample"], **ref.get("shape_keys", {}))
         line = dict(metric="nnz_per_s", value=ref["value"], unit="nnz/s", n_gpus=0, steps=args.steps,
                     warmup=args.warmup, ms_per_step=1e3 * ref["sec_per_epoch"], higher_is_better=True,
                     scaling=scaling, vs_baseline=None, dtype="f64", data="synthetic", config=config,
