@@ -93,7 +93,9 @@ def test_big_shape_slice_against_oracle(case, dt):
     # fp32 drifts further than the fp64 spread on these stiff solves (several halves stop at the 20-iteration
     # cap): measured 0.8-1.3% in the objective after the first outer iteration of the C4-shaped slice, with
     # 175-177 CG iterations against the oracle's 172 -- the per-phase bounds above hold at 1e-4 all the same
-    assert abs(cg - ref["cg"]) <= max(3, ref["cg"] // 20), (cg, ref["cg"])
+    # CG count within the spread of the summation-order variants: 5% in fp64; fp32 measured 3-5 of 172 on
+    # C4s (stiff 20-iteration solves), bound 10%
+    assert abs(cg - ref["cg"]) <= max(3, ref["cg"] // (20 if dt == "f64" else 10)), (cg, ref["cg"])
     assert abs(p.objective() - ref["func1"]) <= (3e-3 if dt == "f64" else 2.5e-2) * abs(ref["func1"]), (cg, ref["cg"])
     if dt == "f64":      # (fp32: the drifted trajectory moves single entries of a by a quarter of the largest one)
         for v in ("a", "b"):
